@@ -1,0 +1,225 @@
+/*
+ * romis_gpu.h -- C-ABI of libromis_gpu.so: the B200 replacement for the body of the reference's
+ * ReSTIR frame, `renderReSTIR` (reference src/rendering/render.cpp:28-62, declared render.h:25-28).
+ *
+ * The reference has no FFI layer: the hot path sits behind plain C++ free functions called from
+ * src/main.cpp:164,220 and src/ui/ui.cpp:161.  A maintainer replaces the body of renderReSTIR by
+ * the marshalling shown in INTEGRATION.md; every entry point below names the reference code it
+ * stands in for.  Plain pointers and sizes only, no C++ or torch types, no exceptions: every call
+ * returns ROMIS_OK (0) or a negative romis_status and leaves a message in romis_last_error().
+ *
+ * A context is bound to ONE CUDA device and is not re-entrant (the reference's CLI mode calls
+ * renderRayTraced from one thread per camera, main.cpp:213-230: create one context per thread).
+ * There is no CPU fallback: romis_create fails when no CUDA device is usable.
+ */
+#ifndef ROMIS_GPU_H
+#define ROMIS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROMIS_ABI_VERSION 1
+
+typedef enum romis_status {
+    ROMIS_OK = 0,
+    ROMIS_ERR_INVALID = -1,     /* bad argument / parameter outside the supported domain */
+    ROMIS_ERR_CUDA = -2,        /* CUDA runtime error (message in romis_last_error) */
+    ROMIS_ERR_STATE = -3,       /* call order (no scene, no frame in flight, ...) */
+    ROMIS_ERR_NOMEM = -4
+} romis_status;
+
+typedef struct romis_ctx romis_ctx;
+
+/* ---- scene: mirrors framework Vertex / Material / Mesh (reference framework/include/framework/mesh.h:14-43) ---- */
+typedef struct romis_vertex {
+    float position[3];
+    float normal[3];
+    float texcoord[2];
+} romis_vertex;
+
+typedef struct romis_material {
+    float kd[3];
+    float ks[3];
+    float shininess;
+    float transparency;
+    int32_t kd_texture;         /* index into the textures passed to romis_upload_scene, -1 = none */
+} romis_material;
+
+typedef struct romis_mesh_desc {
+    const romis_vertex* vertices;
+    uint32_t n_vertices;
+    const uint32_t* triangles;  /* 3 vertex indices per triangle (Mesh::triangles) */
+    uint32_t n_triangles;
+    romis_material material;    /* one material per mesh; geometryId == mesh index (embree_interface.cpp:46-47) */
+} romis_mesh_desc;
+
+typedef struct romis_texture {  /* framework Image (image.h): float RGB, row-major, width*height*3 */
+    const float* pixels;
+    int32_t width, height;
+} romis_texture;
+
+/* ---- lights: tagged POD mirror of PointLight / SegmentLight / ParallelogramLight (reference src/utils/common.h:72-87) ---- */
+enum { ROMIS_LIGHT_POINT = 0, ROMIS_LIGHT_SEGMENT = 1, ROMIS_LIGHT_PARALLELOGRAM = 2 };
+typedef struct romis_light {
+    uint32_t type;
+    float p0[3];    /* point: position      | segment: endpoint0 | parallelogram: v0     */
+    float e1[3];    /*                      | segment: endpoint1 | parallelogram: edge01 */
+    float e2[3];    /*                      |                    | parallelogram: edge02 */
+    float c0[3];    /* point: color         | segment: color0    | parallelogram: color0 */
+    float c1[3];    /*                      | segment: color1    | parallelogram: color1 */
+    float c2[3];    /*                                           | parallelogram: color2 */
+    float c3[3];    /*                                           | parallelogram: color3 */
+} romis_light;
+
+/* ---- parameters: POD mirror of the hot fields of Features (reference src/utils/common.h:89-136), same names ---- */
+typedef struct romis_features {
+    uint32_t enableShading;                 /* common.h:91  */
+    uint32_t enableTextureMapping;          /* common.h:96  */
+    uint32_t initialSamplesVisibilityCheck; /* common.h:104 "visibility reuse" */
+    uint32_t numSamplesInReservoir;         /* common.h:105 N, 1..32 */
+    uint32_t initialLightSamples;           /* common.h:106 M, >= 1 */
+    uint32_t numNeighboursToSample;         /* common.h:107 k, 0..32 */
+    uint32_t spatialResampleRadius;         /* common.h:108 r, pixels */
+    uint32_t unbiasedCombination;           /* common.h:124 */
+    uint32_t spatialReuse;                  /* common.h:125 */
+    uint32_t spatialReuseVisibilityCheck;   /* common.h:126 */
+    uint32_t temporalReuse;                 /* common.h:127 */
+    uint32_t spatialResamplingPasses;       /* common.h:130 P */
+    uint32_t temporalClampM;                /* common.h:131 */
+    uint32_t enableToneMapping;             /* common.h:134 */
+    float gamma;                            /* common.h:135 */
+    float exposure;                         /* common.h:136 */
+} romis_features;
+
+/* Camera: what Trackball::generateRay needs (reference framework/src/trackball.cpp:75-78,105-114).
+ * origin = Trackball::position(); quat = glm::quat(rotationEulerAngles) as (w, x, y, z);
+ * half_height = tan(fovy/2), half_width = aspect * half_height (trackball.cpp:26-27). */
+typedef struct romis_camera {
+    float origin[3];
+    float quat[4];
+    float half_width;
+    float half_height;
+} romis_camera;
+
+/* Counter-based random stream (include/romis_rng.h): one seed per run, one frame index per frame. */
+typedef struct romis_rng {
+    uint64_t seed;
+    uint32_t frame;
+    uint32_t reserved;
+} romis_rng;
+
+/* ---- lifetime ---- */
+/* device_ids/n_devices: exactly one device per context (multi-GPU = one context per GPU, each
+ * owning a row band, see romis_set_band).  Replaces: EmbreeInterface construction + the implicit
+ * process state of the reference (main.cpp:56-65). */
+int romis_create(const int* device_ids, int n_devices, romis_ctx** out);
+void romis_destroy(romis_ctx* ctx);
+/* Last error text of `ctx`; ctx == NULL returns the last romis_create failure. */
+const char* romis_last_error(const romis_ctx* ctx);
+int romis_abi_version(void);
+
+/* ---- scene / lights ---- */
+/* Builds the BVH on the host and uploads geometry, materials and textures.  Replaces
+ * EmbreeInterface::initScene / changeScene (embree_interface.cpp:30-56).  Resets temporal history. */
+int romis_upload_scene(romis_ctx* ctx, const romis_mesh_desc* meshes, int n_meshes,
+                       const romis_texture* textures, int n_textures);
+/* Uploads scene.lights (read fresh every frame by the reference, light.cpp:46-66; call when dirty). */
+int romis_upload_lights(romis_ctx* ctx, const romis_light* lights, int n_lights);
+
+/* ---- the frame ---- */
+/* One ReSTIR frame = renderReSTIR (render.cpp:28-62): primary hits -> initial RIS (+ visibility
+ * reuse) -> temporal reuse -> spatial passes -> shade + tone map.  history_valid == 0 is the
+ * reference's previousFrameGrid == nullptr (render.cpp:35); the returned ReservoirGrid becomes the
+ * device-resident history of the next call.  out_rgb (nullable) receives width*height*3 floats in
+ * Screen::pixels() layout, i.e. row (height-1-y) (screen.cpp:37-43); it may be pageable or pinned
+ * (romis_host_alloc) host memory.  A change of width, height or numSamplesInReservoir drops the
+ * history (the reference would read out of bounds). */
+int romis_render_frame(romis_ctx* ctx, const romis_features* features, const romis_camera* camera,
+                       int width, int height, int history_valid, const romis_rng* rng,
+                       float* out_rgb);
+int romis_reset_history(romis_ctx* ctx);
+/* Same frame, result left on the device; *dev_rgb receives the device pointer of the RGB image
+ * (valid until the next frame).  For callers that present from device memory. */
+int romis_render_frame_device(romis_ctx* ctx, const romis_features* features, const romis_camera* camera,
+                              int width, int height, int history_valid, const romis_rng* rng,
+                              const float** dev_rgb);
+int romis_synchronize(romis_ctx* ctx);
+
+/* ---- row-band sharding (one context per GPU) ---- */
+/* This context renders rows [y0, y1) of the height passed to the frame calls.  Pixels, RNG keys and
+ * the output layout stay in global image coordinates, so N bands reproduce the 1-GPU frame bit for
+ * bit.  Default (or y0 = y1 = 0): whole frame. */
+int romis_set_band(romis_ctx* ctx, int y0, int y1);
+/* Stepwise frame for banded rendering: begin = primary (band + radius halo rows) + initial +
+ * temporal; then per spatial pass: the caller moves halo rows between neighbouring bands
+ * (romis_halo_region, any transport), calls romis_frame_spatial_pass; end = shade + read-back of the
+ * band's rows into out_rgb (full-frame layout; only the band's rows are written). */
+int romis_frame_begin(romis_ctx* ctx, const romis_features* features, const romis_camera* camera,
+                      int width, int height, int history_valid, const romis_rng* rng);
+int romis_frame_spatial_pass(romis_ctx* ctx, int pass);
+int romis_frame_end(romis_ctx* ctx, float* out_rgb);
+/* Halo rows of the reservoir buffer the NEXT spatial pass reads.  which: 0 = send to the band above
+ * (my first `radius` rows... in +y order: rows y0 .. y0+r), 1 = send to the band below (rows y1-r .. y1),
+ * 2 = receive from the band above... see DESIGN.md "row bands".  Regions are contiguous device memory. */
+enum { ROMIS_HALO_SEND_LOW = 0, ROMIS_HALO_SEND_HIGH = 1, ROMIS_HALO_RECV_LOW = 2, ROMIS_HALO_RECV_HIGH = 3 };
+int romis_halo_region(romis_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+/* CUDA stream (cudaStream_t) the context launches on, so the caller can order its transport. */
+int romis_stream(romis_ctx* ctx, void** cuda_stream);
+
+/* ---- parity / debug read-back (SURVEY.md 8b romis_download_reservoirs) ---- */
+enum { ROMIS_PASS_INITIAL = 0, ROMIS_PASS_TEMPORAL = 1, ROMIS_PASS_SPATIAL0 = 2 /* + pass */, ROMIS_PASS_FINAL = 1000 };
+typedef struct romis_reservoir_dump {   /* every pointer nullable; arrays are [N][height][width] (band rows only are written) */
+    uint32_t* light_id;
+    float* u;
+    float* v;
+    float* W;           /* outputWeight */
+    uint32_t* M;        /* sampleNums   */
+    float* position;    /* [N][H][W][3] LightSample::position recomputed from (light, u, v) */
+    float* color;       /* [N][H][W][3] */
+} romis_reservoir_dump;
+typedef struct romis_gbuffer_dump {     /* [height][width] */
+    float* t;           /* Ray::t, FLT_MAX on miss */
+    float* normal;      /* [H][W][3] interpolated, un-normalised */
+    float* texcoord;    /* [H][W][2] */
+    uint32_t* mesh;     /* geometryId; n_meshes on miss */
+} romis_gbuffer_dump;
+/* Capture mode keeps a copy of the reservoir buffer after every stage so that
+ * romis_download_reservoirs can return per-stage state (costs bandwidth; off by default, in which
+ * case only ROMIS_PASS_FINAL is available). */
+int romis_set_capture(romis_ctx* ctx, int enable);
+int romis_download_reservoirs(romis_ctx* ctx, int pass_id, romis_reservoir_dump* out);
+int romis_download_gbuffer(romis_ctx* ctx, romis_gbuffer_dump* out);
+/* Raw ray queries against the uploaded scene: closestHit / anyHit (embree_interface.cpp:58-90).
+ * origins/dirs: n*3 floats, tfar: n floats.  any_hit != 0: hit[i] = occluded.  Otherwise t,u,v,tri
+ * (global triangle index) of the closest hit; hit[i] = 0 leaves the others untouched. */
+int romis_trace_rays(romis_ctx* ctx, const float* origins, const float* dirs, const float* tfar, int n,
+                     int any_hit, uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
+
+/* ---- measurement ---- */
+typedef struct romis_timings {          /* device time of the last frame, milliseconds (CUDA events) */
+    float primary_ms;
+    float initial_ms;
+    float temporal_ms;
+    float spatial_ms[8];
+    float shade_ms;
+    float total_ms;                     /* first kernel start .. last kernel end (no read-back) */
+    int32_t n_spatial;
+    int32_t n_launches;                 /* kernels launched for the frame */
+} romis_timings;
+/* Per-stage events are recorded only when enabled (they break the frame's CUDA graph into
+ * stream launches); total_ms is always available. */
+int romis_set_stage_timing(romis_ctx* ctx, int enable);
+int romis_last_frame_timings(romis_ctx* ctx, romis_timings* out);
+
+/* ---- pinned host memory for out_rgb (Screen::pixels() storage) ---- */
+void* romis_host_alloc(size_t bytes);
+void romis_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROMIS_GPU_H */

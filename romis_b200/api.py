@@ -1,0 +1,249 @@
+"""Python host side of the B200 ReSTIR path: a thin ctypes layer over the C-ABI (include/romis_gpu.h).
+
+`RestirRenderer.render_frame` is the drop-in for the reference's `renderReSTIR`
+(reference src/rendering/render.h:25-28): same inputs (scene, camera, Features, previous-frame grid ->
+`history_valid`), same outputs (Screen::pixels() layout image, the reservoir grid as device-resident
+history).  There is no CPU path: if libromis_gpu.so is missing or CUDA is unusable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .scene import Camera, Features, Scene, LIGHT_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libromis_gpu.so")
+
+EXPORTS = [
+    "romis_abi_version", "romis_create", "romis_destroy", "romis_last_error", "romis_upload_scene", "romis_upload_lights",
+    "romis_render_frame", "romis_render_frame_device", "romis_reset_history", "romis_synchronize", "romis_set_band",
+    "romis_frame_begin", "romis_frame_spatial_pass", "romis_frame_end", "romis_halo_region", "romis_stream",
+    "romis_set_capture", "romis_download_reservoirs", "romis_download_gbuffer", "romis_trace_rays",
+    "romis_set_stage_timing", "romis_last_frame_timings", "romis_host_alloc", "romis_host_free",
+]
+
+
+class RomisError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libromis_gpu.so (built in-tree by `python -m romis_b200.build`).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RomisError(f"{LIB_PATH} is missing: build it with `python -m romis_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ci = C.c_void_p, C.c_int
+    L.romis_last_error.restype = C.c_char_p; L.romis_last_error.argtypes = [vp]
+    L.romis_create.argtypes = [C.POINTER(ci), ci, C.POINTER(vp)]
+    L.romis_destroy.argtypes = [vp]; L.romis_destroy.restype = None
+    L.romis_upload_scene.argtypes = [vp, C.POINTER(abi.romis_mesh_desc), ci, C.POINTER(abi.romis_texture), ci]
+    L.romis_upload_lights.argtypes = [vp, C.POINTER(abi.romis_light), ci]
+    frame_args = [vp, C.POINTER(abi.romis_features), C.POINTER(abi.romis_camera), ci, ci, ci, C.POINTER(abi.romis_rng)]
+    L.romis_render_frame.argtypes = frame_args + [vp]
+    L.romis_render_frame_device.argtypes = frame_args + [C.POINTER(vp)]
+    L.romis_frame_begin.argtypes = frame_args
+    L.romis_frame_spatial_pass.argtypes = [vp, ci]
+    L.romis_frame_end.argtypes = [vp, vp]
+    L.romis_reset_history.argtypes = [vp]; L.romis_synchronize.argtypes = [vp]
+    L.romis_set_band.argtypes = [vp, ci, ci]
+    L.romis_halo_region.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.romis_stream.argtypes = [vp, C.POINTER(vp)]
+    L.romis_set_capture.argtypes = [vp, ci]; L.romis_set_stage_timing.argtypes = [vp, ci]
+    L.romis_download_reservoirs.argtypes = [vp, ci, C.POINTER(abi.romis_reservoir_dump)]
+    L.romis_download_gbuffer.argtypes = [vp, C.POINTER(abi.romis_gbuffer_dump)]
+    L.romis_trace_rays.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]
+    L.romis_last_frame_timings.argtypes = [vp, C.POINTER(abi.romis_timings)]
+    L.romis_host_alloc.restype = vp; L.romis_host_alloc.argtypes = [C.c_size_t]
+    L.romis_host_free.argtypes = [vp]; L.romis_host_free.restype = None
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class ReservoirState:
+    """Per-stage reservoir arrays, [N, H, W(, 3)] (romis_reservoir_dump)."""
+
+    def __init__(self, N, H, W):
+        self.light_id = np.full((N, H, W), 0xFFFFFFFF, np.uint32)
+        self.u = np.zeros((N, H, W), np.float32)
+        self.v = np.zeros((N, H, W), np.float32)
+        self.W = np.zeros((N, H, W), np.float32)
+        self.M = np.zeros((N, H, W), np.uint32)
+        self.position = np.zeros((N, H, W, 3), np.float32)
+        self.color = np.zeros((N, H, W, 3), np.float32)
+
+    def as_abi(self) -> abi.romis_reservoir_dump:
+        d = abi.romis_reservoir_dump()
+        d.light_id = _p(self.light_id, C.c_uint32); d.u = _p(self.u, C.c_float); d.v = _p(self.v, C.c_float)
+        d.W = _p(self.W, C.c_float); d.M = _p(self.M, C.c_uint32)
+        d.position = _p(self.position, C.c_float); d.color = _p(self.color, C.c_float)
+        return d
+
+
+class GBuffer:
+    def __init__(self, H, W):
+        self.t = np.zeros((H, W), np.float32)
+        self.normal = np.zeros((H, W, 3), np.float32)
+        self.texcoord = np.zeros((H, W, 2), np.float32)
+        self.mesh = np.zeros((H, W), np.uint32)
+
+    def as_abi(self) -> abi.romis_gbuffer_dump:
+        d = abi.romis_gbuffer_dump()
+        d.t = _p(self.t, C.c_float); d.normal = _p(self.normal, C.c_float)
+        d.texcoord = _p(self.texcoord, C.c_float); d.mesh = _p(self.mesh, C.c_uint32)
+        return d
+
+
+class PinnedImage:
+    """Page-locked float RGB image in Screen::pixels() layout (romis_host_alloc), exposed as a numpy array."""
+
+    def __init__(self, H, W):
+        L = load_library()
+        self.nbytes = H * W * 3 * 4
+        self.ptr = L.romis_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise RomisError("romis_host_alloc failed")
+        buf = (C.c_float * (H * W * 3)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, np.float32).reshape(H, W, 3)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load_library().romis_host_free(self.ptr); self.ptr = None
+
+
+class RestirRenderer:
+    """One context = one GPU (optionally one row band of the frame)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        ctx = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        rc = self.lib.romis_create(dev, 1, C.byref(ctx))
+        if rc != 0:
+            raise RomisError(f"romis_create failed ({rc}): {self.lib.romis_last_error(None).decode()}")
+        self.ctx = ctx
+        self.W = self.H = self.N = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.romis_destroy(self.ctx); self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RomisError(f"romis error {rc}: {self.lib.romis_last_error(self.ctx).decode()}")
+
+    # ---- scene ----
+    def upload_scene(self, scene: Scene):
+        descs, nm, texs, nt, keep = scene.to_abi()
+        self._check(self.lib.romis_upload_scene(self.ctx, descs, nm, texs, nt))
+        self.upload_lights(scene.lights)
+
+    def upload_lights(self, lights: np.ndarray):
+        a = np.ascontiguousarray(lights, LIGHT_DTYPE)
+        self._check(self.lib.romis_upload_lights(self.ctx, a.ctypes.data_as(C.POINTER(abi.romis_light)), len(a)))
+
+    # ---- frame ----
+    @staticmethod
+    def _cam(camera, W, H) -> abi.romis_camera:
+        return camera.to_abi(W, H) if isinstance(camera, Camera) else camera
+
+    def render_frame(self, features: Features, camera, W: int, H: int, history_valid: bool, seed: int, frame: int,
+                     out: np.ndarray | None = None, want_image: bool = True):
+        """renderReSTIR (reference src/rendering/render.cpp:28-62).  Returns the float RGB image [H, W, 3] in
+        Screen::pixels() layout (row 0 = top), or None with want_image=False (image stays on the device)."""
+        f = features.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
+        if want_image and out is None:
+            out = np.zeros((H, W, 3), np.float32)
+        self._check(self.lib.romis_render_frame(self.ctx, C.byref(f), C.byref(cam), W, H, int(history_valid), C.byref(r),
+                                                out.ctypes.data if want_image else None))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        return out if want_image else None
+
+    def render_frame_device(self, features: Features, camera, W, H, history_valid, seed, frame) -> int:
+        f = features.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
+        dev = C.c_void_p()
+        self._check(self.lib.romis_render_frame_device(self.ctx, C.byref(f), C.byref(cam), W, H, int(history_valid), C.byref(r), C.byref(dev)))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        return dev.value
+
+    def reset_history(self):
+        self._check(self.lib.romis_reset_history(self.ctx))
+
+    def synchronize(self):
+        self._check(self.lib.romis_synchronize(self.ctx))
+
+    # ---- row bands ----
+    def set_band(self, y0: int, y1: int):
+        self._check(self.lib.romis_set_band(self.ctx, y0, y1))
+
+    def frame_begin(self, features: Features, camera, W, H, history_valid, seed, frame):
+        f = features.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
+        self._check(self.lib.romis_frame_begin(self.ctx, C.byref(f), C.byref(cam), W, H, int(history_valid), C.byref(r)))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+
+    def frame_spatial_pass(self, p: int):
+        self._check(self.lib.romis_frame_spatial_pass(self.ctx, p))
+
+    def frame_end(self, out: np.ndarray | None):
+        self._check(self.lib.romis_frame_end(self.ctx, out.ctypes.data if out is not None else None))
+
+    def halo_region(self, which: int):
+        ptr = C.c_void_p(); n = C.c_size_t()
+        self._check(self.lib.romis_halo_region(self.ctx, which, C.byref(ptr), C.byref(n)))
+        return ptr.value or 0, n.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._check(self.lib.romis_stream(self.ctx, C.byref(s)))
+        return s.value or 0
+
+    # ---- parity / measurement ----
+    def set_capture(self, on: bool):
+        self._check(self.lib.romis_set_capture(self.ctx, int(on)))
+
+    def set_stage_timing(self, on: bool):
+        self._check(self.lib.romis_set_stage_timing(self.ctx, int(on)))
+
+    def reservoirs(self, pass_id: int = abi.ROMIS_PASS_FINAL) -> ReservoirState:
+        st = ReservoirState(self.N, self.H, self.W); d = st.as_abi()
+        self._check(self.lib.romis_download_reservoirs(self.ctx, pass_id, C.byref(d)))
+        return st
+
+    def gbuffer(self) -> GBuffer:
+        g = GBuffer(self.H, self.W); d = g.as_abi()
+        self._check(self.lib.romis_download_gbuffer(self.ctx, C.byref(d)))
+        return g
+
+    def timings(self) -> abi.romis_timings:
+        t = abi.romis_timings()
+        self._check(self.lib.romis_last_frame_timings(self.ctx, C.byref(t)))
+        return t
+
+    def trace_rays(self, origins, dirs, tfar, any_hit=False):
+        n = len(tfar)
+        o = np.ascontiguousarray(origins, np.float32); d = np.ascontiguousarray(dirs, np.float32); tf = np.ascontiguousarray(tfar, np.float32)
+        hit = np.zeros(n, np.uint8); t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+        tri = np.full(n, 0xFFFFFFFF, np.uint32)
+        self._check(self.lib.romis_trace_rays(self.ctx, o.ctypes.data, d.ctypes.data, tf.ctypes.data, n, int(any_hit),
+                                              hit.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data, tri.ctypes.data))
+        return hit, t, u, v, tri

@@ -1,0 +1,52 @@
+// k_initial.cu -- initial RIS pass (genInitialSamples / genCanonicalSamples, reference src/scene/light.cpp:39-99).
+#include "reservoir.cuh"
+#include "launch.hpp"
+
+namespace romis {
+
+// ------------------------------------------------------------------------------------------------
+// initial RIS: M candidates per pixel, + visibility reuse
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.y1) return;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const bool es = fr.f.enableShading != 0;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
+    SubRes<NT> r; res_init(r, N);
+    if (sc.n_lights == 0) { res_store(out, y - fr.ey0, x, r, N); return; }          // light.cpp:46: M_j stays 1
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_ENGINE);
+    romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_RAND);
+    uint32_t rc = 0;
+        ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;               // light.cpp:58-60
+    const float invPdf = 1.0f / (float)sc.n_lights;                                 // light.cpp:80
+    const uint32_t Mcand = fr.f.initialLightSamples;
+    for (uint32_t i = 0; i < Mcand; i++) {
+        uint32_t li = (uint32_t)romis_rng_uniform_int(romis_rng_bits(ek, i), 0, sc.n_lights - 1);
+        uint32_t type = __float_as_uint(__ldg(&sc.lights[6 * (size_t)li].x));
+        float u = 0.0f, v = 0.0f;
+        if (type != ROMIS_LIGHT_POINT) u = romis_rand_to_unit(romis_rng_rand(rk, rc++));        // light.cpp:20 / :28
+        if (type == ROMIS_LIGHT_PARALLELOGRAM) v = romis_rand_to_unit(romis_rng_rand(rk, rc++)); // light.cpp:29
+        v3 pos, col; light_sample(sc.lights, li, u, v, pos, col);
+        float w = target_pdf(c, es, pos, col) / invPdf;
+        res_update(r, N, li, u, v, w, rk, rc);
+    }
+    // light.cpp:85-95: visibility reuse zeroes W of occluded samples, otherwise W = (1/pdf)(1/M)wSum
+    res_finish(r, N, sc, c, es);
+    if (fr.f.initialSamplesVisibilityCheck) {
+                ROMIS_FOR_SUB(j, NT, N) {
+            v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
+            if (!visible(sc, c, pos)) r.W[j] = 0.0f;
+        }
+    }
+    res_store(out, y - fr.ey0, x, r, N);
+}
+
+
+void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out) {
+    ROMIS_DISPATCH_N(N, (initial_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, out)));
+}
+}  // namespace romis

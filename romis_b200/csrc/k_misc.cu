@@ -1,0 +1,117 @@
+// k_misc.cu -- primary rays, final shading, ray queries and parity dump kernels.
+#include "reservoir.cuh"
+#include "launch.hpp"
+
+namespace romis {
+
+// ------------------------------------------------------------------------------------------------
+// primary rays -> G-buffer (band rows plus halo rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, GBufDev g, int row0, int row1) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= row1) return;
+    v3 d = gen_ray_dir(fr.cam, x, y, fr.W, fr.H);
+    float t, u, v; uint32_t tri;
+    size_t p = (size_t)(y - fr.ey0) * fr.W + x;
+    if (trace_closest(sc, fr.cam.origin, d, FLT_MAX, t, u, v, tri)) {
+        const float4* a = sc.tri_attr + 4 * (size_t)tri;
+        float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2), a3 = __ldg(a + 3);
+        float w = (1.0f - u) - v;                       // attribute interpolation (w*a + u*b) + v*c, oracle/tracer.h
+        v3 n = add3(add3(scale3(V3(a0.x, a0.y, a0.z), w), scale3(V3(a1.x, a1.y, a1.z), u)), scale3(V3(a2.x, a2.y, a2.z), v));
+        g.tn[p] = make_float4(t, n.x, n.y, n.z);
+        g.mesh[p] = __float_as_uint(a3.w);
+        if (sc.has_textures) {
+            float tu = (w * a0.w + u * a2.w) + v * a3.y;
+            float tv = (w * a1.w + u * a3.x) + v * a3.z;
+            g.uv[p] = make_float2(tu, tv);
+        }
+    } else {                                            // miss: value-initialised RayHit
+        g.tn[p] = make_float4(FLT_MAX, 0.0f, 0.0f, 0.0f);
+        g.mesh[p] = (uint32_t)sc.n_meshes;
+        if (sc.has_textures) g.uv[p] = make_float2(0.0f, 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final shading + tone mapping -> Screen layout (row-flipped float RGB)
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.y1) return;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const bool es = fr.f.enableShading != 0;
+    const int lrow = y - fr.ey0;
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    v3 color = V3(0, 0, 0);
+    for (int j = 0; j < N; j++) {                                                   // render_utils.cpp:56-62
+        uint4 rec = res_rec(in, lrow, j)[x];
+        v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
+        v3 scol = visible(sc, c, pos) ? compute_shading(c, es, pos, col) : V3(0, 0, 0);
+        scol = scale3(scol, __uint_as_float(rec.w));
+        color = add3(color, scol);
+    }
+    color = div3(color, (float)N);                                                  // :63
+    if (fr.f.enableToneMapping) {                                                   // tone_mapping.cpp:8-11
+        float ig = 1.0f / fr.f.gamma;
+        color = V3(romis_powf(1.0f - romis_expf(fr.f.exposure * -color.x), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.y), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.z), ig));
+    }
+    size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;                                   // screen.cpp:37-43
+    rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
+}
+
+// ray queries for the tracer parity tests (romis_trace_rays)
+__global__ void trace_kernel(SceneDev sc, const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ tfar, int n,
+                             int any_hit, uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    v3 oo = V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), dd = V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    if (any_hit) { hit[i] = trace_any(sc, oo, dd, tfar[i]) ? 1 : 0; return; }
+    float tt, uu, vv; uint32_t ti;
+    bool h = trace_closest(sc, oo, dd, tfar[i], tt, uu, vv, ti);
+    hit[i] = h ? 1 : 0;
+    if (h) { t[i] = tt; u[i] = uu; v[i] = vv; tri[i] = ti; }
+}
+
+// unpack a reservoir buffer into the flat arrays of romis_reservoir_dump (parity read-back)
+__global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, uint32_t* light, float* u, float* v, float* W, uint32_t* M,
+                            float* pos, float* col) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.y1) return;
+    for (int j = 0; j < N; j++) {
+        uint4 rec = res_rec(in, y - fr.ey0, j)[x];
+        size_t i = ((size_t)j * fr.H + y) * fr.W + x;
+        if (light) light[i] = rec.x;
+        if (u) u[i] = __uint_as_float(rec.y);
+        if (v) v[i] = __uint_as_float(rec.z);
+        if (W) W[i] = __uint_as_float(rec.w);
+        if (M) M[i] = res_m(in, y - fr.ey0, j)[x];
+        if (pos || col) {
+            v3 p, c; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), p, c);
+            if (pos) { pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
+            if (col) { col[3 * i] = c.x; col[3 * i + 1] = c.y; col[3 * i + 2] = c.z; }
+        }
+    }
+}
+
+
+void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1) {
+    primary_kernel<<<grid, block, 0, s>>>(sc, fr, g, row0, row1);
+}
+void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb) {
+    ROMIS_DISPATCH_N(N, (shade_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rgb)));
+}
+void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
+                  uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {
+    trace_kernel<<<(n + 127) / 128, 128, 0, s>>>(sc, o, d, tfar, n, any_hit, hit, t, u, v, tri);
+}
+void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
+                 uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col) {
+    dump_kernel<<<grid, block, 0, s>>>(sc, fr, in, N, light, u, v, W, M, pos, col);
+}
+}  // namespace romis

@@ -1,0 +1,84 @@
+// k_spatial.cu -- spatial reuse pass (spatialReuse, reference src/rendering/render_utils.cpp:87-140).
+#include "reservoir.cuh"
+#include "launch.hpp"
+
+namespace romis {
+
+// ------------------------------------------------------------------------------------------------
+// spatial reuse, one pass: k neighbours from a (2r+1)^2 window of the previous iteration, self last
+// ------------------------------------------------------------------------------------------------
+template <int NT, bool UNBIASED>
+__global__ void __launch_bounds__(256) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.y1) return;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const bool es = fr.f.enableShading != 0;
+    const int lrow = y - fr.ey0;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
+    constexpr int CAP = SubRes<NT>::CAP;
+    const int k = (int)fr.f.numNeighboursToSample, rad = (int)fr.f.spatialResampleRadius;
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_SPATIAL0 + (uint32_t)pass, pixel, ROMIS_STREAM_ENGINE);
+    romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_SPATIAL0 + (uint32_t)pass, pixel, ROMIS_STREAM_RAND);
+    uint32_t rc = 0;
+    SubRes<NT> r; res_init(r, N);
+    int accepted[UNBIASED ? ROMIS_MAX_K + 1 : 1];   // unbiased: the stream's pixels are revisited for Z (reservoir.cpp:85-93)
+    int ns = 0;
+    const float4 own_tn = g.tn[(size_t)lrow * fr.W + x];
+    for (int nb = 0; nb < k; nb++) {                                                // render_utils.cpp:108-121
+        int dx = romis_rng_uniform_int(romis_rng_bits(ek, 2u * nb), -rad, rad);     // :109 x before y
+        int dy = romis_rng_uniform_int(romis_rng_bits(ek, 2u * nb + 1u), -rad, rad);
+        int nx = min(max(x + dx, 0), fr.W - 1);
+        int ny = min(max(y + dy, 0), fr.H - 1);
+        int nrow = ny - fr.ey0;
+        if (!UNBIASED) {                                                            // :114-118 hard-coded heuristics
+            float4 ntn = g.tn[(size_t)nrow * fr.W + nx];
+            float depthFracDiff = fabsf(1.0f - (ntn.x / own_tn.x));
+            float normalsDot = dot3(V3(ntn.y, ntn.z, ntn.w), V3(own_tn.y, own_tn.z, own_tn.w));
+            if (depthFracDiff > 0.1f || normalsDot < 0.90630778703f) continue;
+        }
+                ROMIS_FOR_SUB(j, NT, N)
+            stream_sample(r, N, sc, c, es, res_rec(in, nrow, j)[nx], res_m(in, nrow, j)[nx], rk, rc);
+        if (UNBIASED) accepted[ns] = ny * fr.W + nx;
+        ns++;
+    }
+        ROMIS_FOR_SUB(j, NT, N)                                        // :124 self last
+        stream_sample(r, N, sc, c, es, res_rec(in, lrow, j)[x], res_m(in, lrow, j)[x], rk, rc);
+    if (UNBIASED) accepted[ns] = y * fr.W + x;
+    ns++;
+    res_take_counts(r, N);
+    if (!UNBIASED) {
+        res_finish(r, N, sc, c, es);
+    } else {
+        // reservoir.cpp:84-103: Z_j = sum of totalM(s) over stream reservoirs s whose OWN pixel sees y_j with pdf > 0
+        uint64_t Z[CAP];
+        v3 spos[CAP], scol[CAP];
+                ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
+        for (int s = 0; s < ns; s++) {
+            int sy = accepted[s] / fr.W, sx = accepted[s] - sy * fr.W;
+            int srow = sy - fr.ey0;
+            PixCtx cs = make_ctx(sc, fr, g, sx, sy);
+            uint64_t tot = 0;
+                        ROMIS_FOR_SUB(j, NT, N) tot += res_m(in, srow, j)[sx];
+                        ROMIS_FOR_SUB(j, NT, N) {
+                float pdf = target_pdf(cs, es, spos[j], scol[j]);
+                if (fr.f.spatialReuseVisibilityCheck) pdf *= visible(sc, cs, spos[j]) ? 1.0f : 0.0f;
+                if (pdf > 0.0f) Z[j] += tot;
+            }
+        }
+                ROMIS_FOR_SUB(j, NT, N) {
+            float pdf = target_pdf(c, es, spos[j], scol[j]);
+            r.W[j] = (pdf == 0.0f || Z[j] == 0ull) ? 0.0f : (1.0f / pdf) * (1.0f / (float)Z[j]) * r.wSum[j];
+        }
+    }
+    res_store(out, lrow, x, r, N);
+}
+
+
+void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                    const ResBuf& in, const ResBuf& out, int pass) {
+    if (unbiased) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
+    else { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
+}
+}  // namespace romis

@@ -1,0 +1,49 @@
+// k_temporal.cu -- temporal reuse pass (temporalReuse, reference src/rendering/render_utils.cpp:142-177).
+#include "reservoir.cuh"
+#include "launch.hpp"
+
+namespace romis {
+
+// ------------------------------------------------------------------------------------------------
+// temporal reuse: same-pixel predecessor, M clamp, biased combine of {current, predecessor}
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.y1) return;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const bool es = fr.f.enableShading != 0;
+    const int lrow = y - fr.ey0;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
+    constexpr int CAP = SubRes<NT>::CAP;
+    uint4 crec[CAP], prec[CAP]; uint32_t cM[CAP], pM[CAP];
+    uint64_t curTotal = 0, prevTotal = 0;
+        ROMIS_FOR_SUB(j, NT, N) {
+        crec[j] = res_rec(cur, lrow, j)[x]; cM[j] = res_m(cur, lrow, j)[x];
+        prec[j] = res_rec(prev, lrow, j)[x]; pM[j] = res_m(prev, lrow, j)[x];
+        curTotal += cM[j]; prevTotal += pM[j];
+    }
+    // render_utils.cpp:156-163: cap = clampM * totalM(cur) + 1; every non-empty predecessor sub-reservoir gets M = cap
+    uint64_t cap = (uint64_t)fr.f.temporalClampM * curTotal + 1ull;
+    if (prevTotal > cap) {
+        uint32_t cap32 = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap;
+                ROMIS_FOR_SUB(j, NT, N) { if (pM[j] != 0u) pM[j] = cap32; }
+    }
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_TEMPORAL, pixel, ROMIS_STREAM_RAND);
+    uint32_t rc = 0;
+    SubRes<NT> r; res_init(r, N);
+        ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, crec[j], cM[j], rk, rc);    // :169 current first
+        ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, prec[j], pM[j], rk, rc);    // then the predecessor
+    res_take_counts(r, N);
+    res_finish(r, N, sc, c, es);
+    res_store(out, lrow, x, r, N);
+}
+
+
+void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out) {
+    ROMIS_DISPATCH_N(N, (temporal_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out)));
+}
+}  // namespace romis

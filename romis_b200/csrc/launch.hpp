@@ -1,0 +1,27 @@
+// launch.hpp -- host-callable launchers of the pass kernels (one translation unit per pass so they build in parallel).
+#pragma once
+#include "device_common.cuh"
+
+namespace romis {
+void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1);
+void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out);
+void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out);
+void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                    const ResBuf& in, const ResBuf& out, int pass);
+void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb);
+void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
+                  uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
+void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
+                 uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col);
+}  // namespace romis
+
+// numSamplesInReservoir 1..4 get register-resident instantiations; anything else the generic one
+#define ROMIS_DISPATCH_N(N, CALL)               \
+    switch (N) {                                \
+        case 1: { constexpr int NT = 1; CALL; } break;  \
+        case 2: { constexpr int NT = 2; CALL; } break;  \
+        case 3: { constexpr int NT = 3; CALL; } break;  \
+        case 4: { constexpr int NT = 4; CALL; } break;  \
+        default: { constexpr int NT = 0; CALL; } break; \
+    }

@@ -1,0 +1,88 @@
+// reservoir.cuh -- register-resident sub-reservoirs shared by the pass kernels; one kernel per pass of the ReSTIR frame (renderReSTIR, reference src/rendering/render.cpp:28-62).
+//
+//   primary_kernel   genPrimaryRayHits      (src/rendering/render_utils.cpp:13-34)   -> G-buffer
+//   initial_kernel   genInitialSamples      (render_utils.cpp:36-52, src/scene/light.cpp:39-99) + visibility reuse
+//   temporal_kernel  temporalReuse          (render_utils.cpp:142-177)
+//   spatial_kernel   spatialReuse, one pass (render_utils.cpp:87-140), biased or unbiased
+//   shade_kernel     final shading loop     (render.cpp:45-57, render_utils.cpp:54-65, tone_mapping.cpp:8-11, screen.cpp:37-43)
+//
+// One thread owns one pixel: the weighted-reservoir stream of a pixel is sequential by definition
+// (every update's accept test depends on the running wSum, reservoir.cpp:22-25), and with >= 2 M pixels
+// per frame the grid is wide enough that no intra-pixel parallelism is needed.  Random draws are
+// addressed by (pixel, stage, stream, counter) (include/romis_rng.h), so the result does not depend on
+// the launch shape, the band split or the pass order of other pixels.
+//
+// NT > 0: numSamplesInReservoir is the compile-time constant NT and sub-reservoirs live in registers.
+// NT == 0: runtime N <= 32, sub-reservoirs in local memory (generic fallback).
+#pragma once
+#include "device_common.cuh"
+
+namespace romis {
+
+// Loop over sub-reservoirs: compile-time trip count (fully unrolled, register-resident) when NT > 0,
+// runtime trip count over local-memory arrays in the generic NT == 0 fallback.
+#define ROMIS_FOR_SUB(j, NT, N) _Pragma("unroll") for (int j = 0; j < ((NT) > 0 ? (NT) : (N)); j++)
+
+template <int NT> struct SubRes {
+    static constexpr int CAP = NT > 0 ? NT : 32;
+    uint32_t light[CAP]; float u[CAP], v[CAP], W[CAP], wSum[CAP];
+    uint32_t M[CAP];
+    uint64_t cnt[CAP];
+};
+
+// Reservoir::Reservoir (reservoir.h:29-32)
+template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N) {
+        ROMIS_FOR_SUB(j, NT, N) {
+        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull;
+    }
+}
+
+// Reservoir::update (reservoir.cpp:10-32); returns the sub-reservoir that took the sample
+template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N, uint32_t light, float u, float v, float weight,
+                                                            romis_stream_key rk, uint32_t& rc) {
+    int idx = 0; float smallest = FLT_MAX;
+        ROMIS_FOR_SUB(j, NT, N) { if (r.wSum[j] < smallest) { idx = j; smallest = r.wSum[j]; } }
+    float rnd = romis_rand_to_unit(romis_rng_rand(rk, rc++));
+        ROMIS_FOR_SUB(j, NT, N) {
+        if (j == idx) {
+            r.M[j] += 1u;
+            r.wSum[j] += weight;
+            if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; }
+        }
+    }
+    return idx;
+}
+
+template <int NT> __device__ __forceinline__ void res_store(const ResBuf& b, int lrow, int x, const SubRes<NT>& r, int N) {
+        ROMIS_FOR_SUB(j, NT, N) {
+        res_rec(b, lrow, j)[x] = make_uint4(r.light[j], __float_as_uint(r.u[j]), __float_as_uint(r.v[j]), __float_as_uint(r.W[j]));
+        res_m(b, lrow, j)[x] = r.M[j];
+    }
+}
+
+// W_j = pdf == 0 ? 0 : (1/pdf) * (1/M_j) * wSum_j   (light.cpp:89-93, reservoir.cpp:57-65)
+template <int NT> __device__ __forceinline__ void res_finish(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es) {
+        ROMIS_FOR_SUB(j, NT, N) {
+        v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
+        float pdf = target_pdf(c, es, pos, col);
+        r.W[j] = (pdf == 0.0f) ? 0.0f : (1.0f / pdf) * (1.0f / (float)r.M[j]) * r.wSum[j];
+    }
+}
+
+// One stream entry of combineBiased / combineUnbiased (reservoir.cpp:42-53): w = (pdf * W_i) * float(M_i)
+template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es,
+                                                                uint4 rec, uint32_t Mi, romis_stream_key rk, uint32_t& rc) {
+    float u = __uint_as_float(rec.y), v = __uint_as_float(rec.z), Wi = __uint_as_float(rec.w);
+    v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col);
+    float pdf = target_pdf(c, es, pos, col);
+    int idx = res_update(r, N, rec.x, u, v, pdf * Wi * (float)Mi, rk, rc);
+        if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] += (uint64_t)Mi; } }
+    else r.cnt[idx] += (uint64_t)Mi;
+}
+
+// sampleNums = routed sums of the sources' M (reservoir.cpp:54,82); saturates at 2^32-1
+template <int NT> __device__ __forceinline__ void res_take_counts(SubRes<NT>& r, int N) {
+        ROMIS_FOR_SUB(j, NT, N) r.M[j] = r.cnt[j] > 0xffffffffull ? 0xffffffffu : (uint32_t)r.cnt[j];
+}
+
+}  // namespace romis

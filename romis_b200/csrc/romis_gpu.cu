@@ -1,0 +1,621 @@
+// romis_gpu.cu -- implementation of the C-ABI declared in include/romis_gpu.h.
+//
+// Host side of the B200 ReSTIR path: context, scene/light upload (host BVH build, flattening into
+// device tables), the per-frame launch sequence (one kernel per pass, kernels.cuh), row-band state for
+// multi-GPU sharding, parity read-backs and CUDA-event timing.  No CPU rendering path exists here: if
+// CUDA is unusable romis_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "romis_gpu.h"
+#include "launch.hpp"
+
+using namespace romis;
+
+namespace {
+std::mutex g_err_mutex;
+std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n ? n : 16);
+        if (e == cudaSuccess) bytes = n ? n : 16;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+}  // namespace
+
+struct romis_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // scene
+    bool has_scene = false;
+    DevBuf nodes, tri_geom, tri_attr, materials, tex_pixels, tex_desc, lights;
+    SceneDev sc{};
+    int n_tris = 0;
+
+    // frame geometry
+    int W = 0, H = 0, N = 0;
+    int band_y0 = 0, band_y1 = 0;       // requested band (0,0 = whole frame)
+    int y0 = 0, y1 = 0, ey0 = 0, ey1 = 0, halo = 0;
+    size_t row_stride = 0;
+    DevBuf gb_tn, gb_mesh, gb_uv, rgb;
+    DevBuf res[3];
+    int hist = 2, cur = 0, spare = 1;   // indices into res[]: previous frame's final state / newest state / free work buffer
+    bool history_valid = false;
+
+    // stepwise frame state
+    bool in_frame = false;
+    FrameDev fr{};
+    int next_pass = 0;
+    int n_launches = 0;
+
+    // parity capture
+    bool capture = false;
+    std::map<int, DevBuf> captured;
+
+    // timing
+    bool stage_timing = false;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_stage;  // begin, after primary, after initial, after temporal, after spatial p..., after shade
+    struct Mark { int kind; int idx; };
+    std::vector<Mark> marks;
+    romis_timings last{};
+    bool timings_pending = false;
+};
+
+#define RCHECK(ctx, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+            return ROMIS_ERR_CUDA;                                                                \
+        }                                                                                         \
+    } while (0)
+
+static int fail(romis_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+static float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+static ResBuf resbuf(const romis_ctx* c, int i) {
+    ResBuf b; b.base = (unsigned char*)c->res[i].p; b.row_stride = c->row_stride; b.W = c->W; b.N = c->N; return b;
+}
+static GBufDev gbuf(const romis_ctx* c) {
+    GBufDev g; g.tn = (float4*)c->gb_tn.p; g.mesh = (uint32_t*)c->gb_mesh.p; g.uv = (float2*)c->gb_uv.p; return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_abi_version(void) { return ROMIS_ABI_VERSION; }
+
+extern "C" const char* romis_last_error(const romis_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_create_err;
+    return copy.c_str();
+}
+
+extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** out) {
+    auto set_err = [](const std::string& s) { std::lock_guard<std::mutex> lk(g_err_mutex); g_create_err = s; };
+    if (!out) { set_err("out == NULL"); return ROMIS_ERR_INVALID; }
+    *out = nullptr;
+    if (n_devices != 1 && !(n_devices == 0 && device_ids == nullptr)) {
+        set_err("one context drives exactly one device; create one context per GPU and give each a row band (romis_set_band)");
+        return ROMIS_ERR_INVALID;
+    }
+    int dev = (n_devices == 1 && device_ids) ? device_ids[0] : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_err(std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return ROMIS_ERR_CUDA;
+    }
+    if (dev < 0 || dev >= count) { set_err("device id out of range"); return ROMIS_ERR_INVALID; }
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) { set_err(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return ROMIS_ERR_CUDA; }
+    romis_ctx* c = new (std::nothrow) romis_ctx();
+    if (!c) { set_err("out of host memory"); return ROMIS_ERR_NOMEM; }
+    c->device = dev;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
+    if (e != cudaSuccess) { set_err(std::string("context setup: ") + cudaGetErrorString(e)); delete c; return ROMIS_ERR_CUDA; }
+    *out = c;
+    return ROMIS_OK;
+}
+
+extern "C" void romis_destroy(romis_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2]}) b->release();
+    for (auto& kv : c->captured) kv.second.release();
+    for (cudaEvent_t e : c->ev_stage) cudaEventDestroy(e);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int romis_stream(romis_ctx* c, void** s) {
+    if (!c || !s) return ROMIS_ERR_INVALID;
+    *s = (void*)c->stream; return ROMIS_OK;
+}
+
+extern "C" int romis_synchronize(romis_ctx* c) {
+    if (!c) return ROMIS_ERR_INVALID;
+    RCHECK(c, cudaSetDevice(c->device));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    return ROMIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_upload_scene(romis_ctx* c, const romis_mesh_desc* meshes, int n_meshes,
+                                  const romis_texture* textures, int n_textures) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (n_meshes < 0 || n_textures < 0 || (n_meshes > 0 && !meshes) || (n_textures > 0 && !textures))
+        return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: bad arguments");
+    RCHECK(c, cudaSetDevice(c->device));
+    size_t ntri = 0;
+    for (int m = 0; m < n_meshes; m++) {
+        if ((meshes[m].n_triangles && !meshes[m].triangles) || (meshes[m].n_vertices && !meshes[m].vertices))
+            return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: mesh with null arrays");
+        for (uint32_t t = 0; t < 3 * meshes[m].n_triangles; t++)
+            if (meshes[m].triangles[t] >= meshes[m].n_vertices) return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: vertex index out of range");
+        ntri += meshes[m].n_triangles;
+    }
+    if (ntri > 0x7fffffffu / 16) return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: too many triangles");
+    // global triangle order = mesh order, then the mesh's triangle order (geomID = mesh index, embree_interface.cpp:46-47)
+    std::vector<float> verts(9 * ntri + 1);
+    std::vector<float4> attr(4 * ntri + 1);
+    size_t g = 0;
+    for (int m = 0; m < n_meshes; m++) {
+        for (uint32_t t = 0; t < meshes[m].n_triangles; t++, g++) {
+            const romis_vertex* v[3];
+            for (int k = 0; k < 3; k++) { v[k] = &meshes[m].vertices[meshes[m].triangles[3 * t + k]]; std::memcpy(&verts[9 * g + 3 * k], v[k]->position, 12); }
+            attr[4 * g + 0] = make_float4(v[0]->normal[0], v[0]->normal[1], v[0]->normal[2], v[0]->texcoord[0]);
+            attr[4 * g + 1] = make_float4(v[1]->normal[0], v[1]->normal[1], v[1]->normal[2], v[0]->texcoord[1]);
+            attr[4 * g + 2] = make_float4(v[2]->normal[0], v[2]->normal[1], v[2]->normal[2], v[1]->texcoord[0]);
+            attr[4 * g + 3] = make_float4(v[1]->texcoord[1], v[2]->texcoord[0], v[2]->texcoord[1], u2f((uint32_t)m));
+        }
+    }
+    Bvh bvh = build_bvh(verts.data(), (int)ntri);
+    if (bvh.max_depth >= ROMIS_STACK) return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: BVH deeper than the traversal stack");
+
+    std::vector<float4> mats(2 * (size_t)(n_meshes + 1));
+    bool any_tex = false;
+    for (int m = 0; m < n_meshes; m++) {
+        const romis_material& mt = meshes[m].material;
+        int tex = (mt.kd_texture >= 0 && mt.kd_texture < n_textures) ? mt.kd_texture : -1;
+        any_tex |= tex >= 0;
+        mats[2 * m] = make_float4(mt.kd[0], mt.kd[1], mt.kd[2], mt.shininess);
+        mats[2 * m + 1] = make_float4(mt.ks[0], mt.ks[1], mt.ks[2], u2f((uint32_t)tex));
+    }
+    // miss pixels carry a value-initialised Material: kd = ks = 0, shininess = 1 (mesh.h:22-34)
+    mats[2 * n_meshes] = make_float4(0, 0, 0, 1.0f);
+    mats[2 * n_meshes + 1] = make_float4(0, 0, 0, u2f(0xffffffffu));
+
+    std::vector<float> texpx; std::vector<int4> texdesc((size_t)std::max(1, n_textures));
+    for (int t = 0; t < n_textures; t++) {
+        if (!textures[t].pixels || textures[t].width <= 0 || textures[t].height <= 0) return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: bad texture");
+        size_t n = (size_t)textures[t].width * textures[t].height * 3;
+        texdesc[t] = make_int4((int)texpx.size(), textures[t].width, textures[t].height, 0);
+        texpx.insert(texpx.end(), textures[t].pixels, textures[t].pixels + n);
+    }
+
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    RCHECK(c, c->nodes.ensure(bvh.nodes.size() * sizeof(BvhNode)));
+    RCHECK(c, c->tri_geom.ensure(std::max<size_t>(1, bvh.tris.size()) * sizeof(TriGeom)));
+    RCHECK(c, c->tri_attr.ensure(attr.size() * sizeof(float4)));
+    RCHECK(c, c->materials.ensure(mats.size() * sizeof(float4)));
+    RCHECK(c, c->tex_pixels.ensure(std::max<size_t>(1, texpx.size()) * sizeof(float)));
+    RCHECK(c, c->tex_desc.ensure(texdesc.size() * sizeof(int4)));
+    RCHECK(c, cudaMemcpy(c->nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    if (!bvh.tris.empty()) RCHECK(c, cudaMemcpy(c->tri_geom.p, bvh.tris.data(), bvh.tris.size() * sizeof(TriGeom), cudaMemcpyHostToDevice));
+    RCHECK(c, cudaMemcpy(c->tri_attr.p, attr.data(), attr.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    RCHECK(c, cudaMemcpy(c->materials.p, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (!texpx.empty()) RCHECK(c, cudaMemcpy(c->tex_pixels.p, texpx.data(), texpx.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RCHECK(c, cudaMemcpy(c->tex_desc.p, texdesc.data(), texdesc.size() * sizeof(int4), cudaMemcpyHostToDevice));
+
+    c->sc.nodes = (const BvhNode*)c->nodes.p;
+    c->sc.tri_geom = (const float4*)c->tri_geom.p;
+    c->sc.tri_attr = (const float4*)c->tri_attr.p;
+    c->sc.materials = (const float4*)c->materials.p;
+    c->sc.tex_pixels = (const float*)c->tex_pixels.p;
+    c->sc.tex_desc = (const int4*)c->tex_desc.p;
+    c->sc.n_meshes = n_meshes;
+    c->sc.has_textures = any_tex ? 1 : 0;
+    c->n_tris = (int)ntri;
+    c->has_scene = true;
+    c->history_valid = false;
+    c->W = c->H = c->N = 0;             // G-buffer layout depends on has_textures: force re-allocation
+    return ROMIS_OK;
+}
+
+// Light record: six float4, ordered so that a point light needs the first two and a segment light the first four.
+//   {type, p0} {c0, c3.x} {e1, c3.y} {c1, c3.z} {e2, 0} {c2, 0}
+static void pack_light(const romis_light& l, float4* r) {
+    r[0] = make_float4(u2f((uint32_t)l.type), l.p0[0], l.p0[1], l.p0[2]);
+    r[1] = make_float4(l.c0[0], l.c0[1], l.c0[2], l.c3[0]);
+    r[2] = make_float4(l.e1[0], l.e1[1], l.e1[2], l.c3[1]);
+    r[3] = make_float4(l.c1[0], l.c1[1], l.c1[2], l.c3[2]);
+    r[4] = make_float4(l.e2[0], l.e2[1], l.e2[2], 0.0f);
+    r[5] = make_float4(l.c2[0], l.c2[1], l.c2[2], 0.0f);
+}
+
+extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (n < 0 || (n > 0 && !lights)) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: bad arguments");
+    RCHECK(c, cudaSetDevice(c->device));
+    std::vector<float4> rec(6 * (size_t)std::max(1, n));
+    for (int i = 0; i < n; i++) {
+        if (lights[i].type > ROMIS_LIGHT_PARALLELOGRAM) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: unknown light type");
+        pack_light(lights[i], &rec[6 * (size_t)i]);
+    }
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    RCHECK(c, c->lights.ensure(rec.size() * sizeof(float4)));
+    RCHECK(c, cudaMemcpy(c->lights.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    c->sc.lights = (const float4*)c->lights.p;
+    c->sc.n_lights = n;
+    return ROMIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_set_band(romis_ctx* c, int y0, int y1) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (y0 < 0 || y1 < y0) return fail(c, ROMIS_ERR_INVALID, "romis_set_band: need 0 <= y0 <= y1");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_set_band: frame in flight");
+    if (y0 != c->band_y0 || y1 != c->band_y1) { c->band_y0 = y0; c->band_y1 = y1; c->W = c->H = c->N = 0; c->history_valid = false; }
+    return ROMIS_OK;
+}
+
+extern "C" int romis_reset_history(romis_ctx* c) { if (!c) return ROMIS_ERR_INVALID; c->history_valid = false; return ROMIS_OK; }
+extern "C" int romis_set_capture(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->capture = on != 0; return ROMIS_OK; }
+extern "C" int romis_set_stage_timing(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->stage_timing = on != 0; return ROMIS_OK; }
+
+static int validate(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H, const romis_rng* rng) {
+    if (!f || !cam || !rng) return fail(c, ROMIS_ERR_INVALID, "null features / camera / rng");
+    if (W < 1 || H < 1 || (long long)W * H > 0x7fffffffLL) return fail(c, ROMIS_ERR_INVALID, "bad resolution");
+    if (f->numSamplesInReservoir < 1 || f->numSamplesInReservoir > 32) return fail(c, ROMIS_ERR_INVALID, "numSamplesInReservoir must be 1..32 (ui.cpp:305)");
+    if (f->initialLightSamples < 1) return fail(c, ROMIS_ERR_INVALID, "initialLightSamples must be >= 1");
+    if (f->numNeighboursToSample > ROMIS_MAX_K) return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample must be <= 32");
+    if (f->spatialResampleRadius > 4096) return fail(c, ROMIS_ERR_INVALID, "spatialResampleRadius must be <= 4096");
+    if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
+    return ROMIS_OK;
+}
+
+static cudaError_t mark(romis_ctx* c, int kind, int idx) {
+    if (!c->stage_timing) return cudaSuccess;
+    size_t i = c->marks.size();
+    if (i >= c->ev_stage.size()) { cudaEvent_t e; cudaError_t r = cudaEventCreate(&e); if (r != cudaSuccess) return r; c->ev_stage.push_back(e); }
+    c->marks.push_back({kind, idx});
+    return cudaEventRecord(c->ev_stage[i], c->stream);
+}
+
+static int capture_stage(romis_ctx* c, int pass_id, int buf) {
+    if (!c->capture) return ROMIS_OK;
+    DevBuf& d = c->captured[pass_id];
+    RCHECK(c, d.ensure(c->res[buf].bytes));
+    RCHECK(c, cudaMemcpyAsync(d.p, c->res[buf].p, c->res[buf].bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return ROMIS_OK;
+}
+
+static const dim3 kBlock(32, 8);
+static dim3 grid_for(int W, int rows) { return dim3((W + kBlock.x - 1) / kBlock.x, (rows + kBlock.y - 1) / kBlock.y); }
+
+extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
+                                 int history_valid, const romis_rng* rng) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_begin: previous frame not ended");
+    int rc = validate(c, f, cam, W, H, rng);
+    if (rc) return rc;
+    RCHECK(c, cudaSetDevice(c->device));
+    const int N = (int)f->numSamplesInReservoir;
+    int y0 = 0, y1 = H;
+    if (c->band_y1 > c->band_y0) { y0 = c->band_y0; y1 = c->band_y1; if (y1 > H) return fail(c, ROMIS_ERR_INVALID, "band exceeds the image height"); }
+    const int halo = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
+    if (W != c->W || H != c->H || N != c->N || halo > c->halo || y0 != c->y0 || y1 != c->y1) {
+        // (re)allocate; a change of resolution or N drops the temporal history
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+        c->W = W; c->H = H; c->N = N; c->halo = halo; c->y0 = y0; c->y1 = y1;
+        c->ey0 = std::max(0, y0 - halo); c->ey1 = std::min(H, y1 + halo);
+        const size_t rows = (size_t)(c->ey1 - c->ey0), px = rows * W;
+        c->row_stride = (((size_t)W * 20 * N) + 15) & ~(size_t)15;
+        RCHECK(c, c->gb_tn.ensure(px * sizeof(float4)));
+        RCHECK(c, c->gb_mesh.ensure(px * sizeof(uint32_t)));
+        RCHECK(c, c->gb_uv.ensure(c->sc.has_textures ? px * sizeof(float2) : 16));
+        RCHECK(c, c->rgb.ensure((size_t)W * H * 3 * sizeof(float)));
+        for (int i = 0; i < 3; i++) {
+            RCHECK(c, c->res[i].ensure(rows * c->row_stride));
+            RCHECK(c, cudaMemsetAsync(c->res[i].p, 0, c->res[i].bytes, c->stream));
+        }
+        RCHECK(c, cudaMemsetAsync(c->rgb.p, 0, c->rgb.bytes, c->stream));
+        c->history_valid = false;
+        for (auto& kv : c->captured) kv.second.release();
+        c->captured.clear();
+    }
+    if (!history_valid) c->history_valid = false;
+
+    FrameDev& fr = c->fr;
+    fr.cam.origin.x = cam->origin[0]; fr.cam.origin.y = cam->origin[1]; fr.cam.origin.z = cam->origin[2];
+    fr.cam.qw = cam->quat[0]; fr.cam.qx = cam->quat[1]; fr.cam.qy = cam->quat[2]; fr.cam.qz = cam->quat[3];
+    fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
+    fr.f = *f; fr.seed = rng->seed; fr.frame = rng->frame;
+    fr.W = W; fr.H = H; fr.y0 = c->y0; fr.y1 = c->y1; fr.ey0 = c->ey0; fr.ey1 = c->ey1;
+    // halo rows are only meaningful up to this frame's radius
+    const int r_now = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
+    const int pey0 = std::max(0, c->y0 - r_now), pey1 = std::min(H, c->y1 + r_now);
+
+    c->marks.clear(); c->n_launches = 0; c->timings_pending = true;
+    std::memset(&c->last, 0, sizeof c->last);
+    RCHECK(c, cudaEventRecord(c->ev_begin, c->stream));
+    RCHECK(c, mark(c, 0, 0));
+
+    // work buffers: the two that are not the history
+    const int w0 = (c->hist + 1) % 3;
+    c->spare = (c->hist + 2) % 3;
+    const dim3 gOwn = grid_for(W, c->y1 - c->y0);
+
+    // 1. primary rays for band + halo rows (the halo G-buffer is re-traced locally instead of exchanged)
+    launch_primary(c->stream, grid_for(W, pey1 - pey0), kBlock, c->sc, fr, gbuf(c), pey0, pey1);
+    c->n_launches++;
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, mark(c, 1, 0));
+
+    // 2. initial RIS (+ visibility reuse)
+    launch_initial(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
+    c->n_launches++;
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, mark(c, 2, 0));
+    if ((rc = capture_stage(c, ROMIS_PASS_INITIAL, w0))) return rc;
+
+    // 3. temporal reuse (in place on w0; reads the history)
+    if (f->temporalReuse && c->history_valid) {
+        launch_temporal(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0));
+        c->n_launches++;
+        RCHECK(c, cudaGetLastError());
+        RCHECK(c, mark(c, 3, 0));
+        if ((rc = capture_stage(c, ROMIS_PASS_TEMPORAL, w0))) return rc;
+    }
+    c->cur = w0;
+    c->next_pass = 0;
+    c->in_frame = true;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_spatial_pass: no frame in flight");
+    if (!c->fr.f.spatialReuse || pass != c->next_pass || pass >= (int)c->fr.f.spatialResamplingPasses)
+        return fail(c, ROMIS_ERR_STATE, "romis_frame_spatial_pass: unexpected pass index");
+    RCHECK(c, cudaSetDevice(c->device));
+    // ping-pong between the two work buffers; the history buffer is never written during a frame
+    const int in = c->cur, out = c->spare;
+    const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
+    launch_spatial(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass);
+    c->n_launches++;
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, mark(c, 4, pass));
+    int rc = capture_stage(c, ROMIS_PASS_SPATIAL0 + pass, out);
+    if (rc) return rc;
+    c->spare = in;
+    c->cur = out;
+    c->next_pass++;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_end: no frame in flight");
+    if (c->fr.f.spatialReuse && c->next_pass != (int)c->fr.f.spatialResamplingPasses)
+        return fail(c, ROMIS_ERR_STATE, "romis_frame_end: spatial passes missing");
+    RCHECK(c, cudaSetDevice(c->device));
+    const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
+    launch_shade(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, c->cur), (float*)c->rgb.p);
+    c->n_launches++;
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, mark(c, 5, 0));
+    RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
+    int rc = capture_stage(c, ROMIS_PASS_FINAL, c->cur);
+    if (rc) return rc;
+    // the returned grid becomes next frame's previousFrameGrid (main.cpp:165)
+    c->hist = c->cur;
+    c->history_valid = true;
+    c->in_frame = false;
+    if (out_rgb) {
+        // band rows [y0, y1) live at image rows [H - y1, H - y0) of the flipped Screen layout: one contiguous range
+        size_t off = (size_t)(c->H - c->y1) * c->W * 3, cnt = (size_t)(c->y1 - c->y0) * c->W * 3;
+        RCHECK(c, cudaMemcpyAsync(out_rgb + off, (const float*)c->rgb.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    return ROMIS_OK;
+}
+
+static int render_common(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H, int history_valid,
+                         const romis_rng* rng, float* out_rgb) {
+    int rc = romis_frame_begin(c, f, cam, W, H, history_valid, rng);
+    if (rc) return rc;
+    if (f->spatialReuse)
+        for (int p = 0; p < (int)f->spatialResamplingPasses; p++)
+            if ((rc = romis_frame_spatial_pass(c, p))) { c->in_frame = false; return rc; }
+    rc = romis_frame_end(c, out_rgb);
+    if (rc) c->in_frame = false;
+    return rc;
+}
+
+extern "C" int romis_render_frame(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
+                                  int history_valid, const romis_rng* rng, float* out_rgb) {
+    if (!c) return ROMIS_ERR_INVALID;
+    int rc = render_common(c, f, cam, W, H, history_valid, rng, out_rgb);
+    if (rc == ROMIS_OK && !out_rgb) RCHECK(c, cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
+                                         int history_valid, const romis_rng* rng, const float** dev_rgb) {
+    if (!c) return ROMIS_ERR_INVALID;
+    int rc = render_common(c, f, cam, W, H, history_valid, rng, nullptr);
+    if (rc == ROMIS_OK && dev_rgb) *dev_rgb = (const float*)c->rgb.p;
+    return rc;
+}
+
+extern "C" int romis_halo_region(romis_ctx* c, int which, void** dev_ptr, size_t* bytes) {
+    if (!c || !dev_ptr || !bytes) return ROMIS_ERR_INVALID;
+    if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_halo_region: no frame in flight");
+    const int r = c->fr.f.spatialReuse ? (int)c->fr.f.spatialResampleRadius : 0;
+    if (c->y1 - c->y0 < r) return fail(c, ROMIS_ERR_INVALID, "band has fewer rows than the spatial radius");
+    int row0 = 0, rows = 0;     // local rows (relative to ey0) of the buffer the next spatial pass reads
+    switch (which) {
+        case ROMIS_HALO_SEND_LOW:  rows = c->y0 > 0 ? r : 0; row0 = c->y0 - c->ey0; break;
+        case ROMIS_HALO_RECV_LOW:  rows = c->y0 - std::max(0, c->y0 - r); row0 = (c->y0 - rows) - c->ey0; break;
+        case ROMIS_HALO_SEND_HIGH: rows = c->y1 < c->H ? r : 0; row0 = (c->y1 - rows) - c->ey0; break;
+        case ROMIS_HALO_RECV_HIGH: rows = std::min(c->H, c->y1 + r) - c->y1; row0 = c->y1 - c->ey0; break;
+        default: return fail(c, ROMIS_ERR_INVALID, "romis_halo_region: bad selector");
+    }
+    *dev_ptr = (unsigned char*)c->res[c->cur].p + (size_t)row0 * c->row_stride;
+    *bytes = (size_t)rows * c->row_stride;
+    return ROMIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
+    if (!c || !out) return ROMIS_ERR_INVALID;
+    RCHECK(c, cudaSetDevice(c->device));
+    if (c->timings_pending) {
+        RCHECK(c, cudaEventSynchronize(c->ev_end));
+        romis_timings t; std::memset(&t, 0, sizeof t);
+        RCHECK(c, cudaEventElapsedTime(&t.total_ms, c->ev_begin, c->ev_end));
+        for (size_t i = 1; i < c->marks.size(); i++) {
+            float ms = 0; RCHECK(c, cudaEventElapsedTime(&ms, c->ev_stage[i - 1], c->ev_stage[i]));
+            switch (c->marks[i].kind) {
+                case 1: t.primary_ms = ms; break;
+                case 2: t.initial_ms = ms; break;
+                case 3: t.temporal_ms = ms; break;
+                case 4: if (c->marks[i].idx < 8) t.spatial_ms[c->marks[i].idx] = ms; t.n_spatial = std::max(t.n_spatial, c->marks[i].idx + 1); break;
+                case 5: t.shade_ms = ms; break;
+            }
+        }
+        t.n_launches = c->n_launches;
+        c->last = t; c->timings_pending = false;
+    }
+    *out = c->last;
+    return ROMIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity read-backs
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_download_reservoirs(romis_ctx* c, int pass_id, romis_reservoir_dump* out) {
+    if (!c || !out) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_download_reservoirs: frame in flight");
+    if (!c->W) return fail(c, ROMIS_ERR_STATE, "romis_download_reservoirs: no frame rendered");
+    RCHECK(c, cudaSetDevice(c->device));
+    const unsigned char* src = nullptr;
+    if (c->capture) {
+        auto it = c->captured.find(pass_id);
+        if (it != c->captured.end()) src = (const unsigned char*)it->second.p;
+    } else if (pass_id == ROMIS_PASS_FINAL && c->history_valid) src = (const unsigned char*)c->res[c->hist].p;
+    if (!src) return fail(c, ROMIS_ERR_STATE, "romis_download_reservoirs: pass not captured (romis_set_capture) or not run this frame");
+    const size_t n = (size_t)c->N * c->W * c->H;
+    struct Slot { void* host; size_t elem; void* dev; } slots[7] = {
+        {out->light_id, 4, nullptr}, {out->u, 4, nullptr}, {out->v, 4, nullptr}, {out->W, 4, nullptr}, {out->M, 4, nullptr},
+        {out->position, 12, nullptr}, {out->color, 12, nullptr}};
+    int rc = ROMIS_OK;
+    for (auto& s : slots) if (s.host) {
+        if (cudaMalloc(&s.dev, n * s.elem) != cudaSuccess) { rc = fail(c, ROMIS_ERR_NOMEM, "romis_download_reservoirs: device scratch"); break; }
+        cudaMemsetAsync(s.dev, 0, n * s.elem, c->stream);
+    }
+    if (rc == ROMIS_OK) {
+        ResBuf b; b.base = (unsigned char*)src; b.row_stride = c->row_stride; b.W = c->W; b.N = c->N;
+        launch_dump(c->stream, grid_for(c->W, c->y1 - c->y0), kBlock, c->sc, c->fr, b, c->N, (uint32_t*)slots[0].dev, (float*)slots[1].dev,
+                    (float*)slots[2].dev, (float*)slots[3].dev, (uint32_t*)slots[4].dev, (float*)slots[5].dev, (float*)slots[6].dev);
+        cudaError_t e = cudaGetLastError();
+        for (auto& s : slots) if (s.host && e == cudaSuccess) e = cudaMemcpyAsync(s.host, s.dev, n * s.elem, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(c, ROMIS_ERR_CUDA, std::string("romis_download_reservoirs: ") + cudaGetErrorString(e));
+    }
+    for (auto& s : slots) if (s.dev) cudaFree(s.dev);
+    return rc;
+}
+
+extern "C" int romis_download_gbuffer(romis_ctx* c, romis_gbuffer_dump* out) {
+    if (!c || !out) return ROMIS_ERR_INVALID;
+    if (!c->W) return fail(c, ROMIS_ERR_STATE, "romis_download_gbuffer: no frame rendered");
+    RCHECK(c, cudaSetDevice(c->device));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    const size_t rows = (size_t)(c->y1 - c->y0), px = rows * c->W, off = (size_t)(c->y0 - c->ey0) * c->W;
+    std::vector<float4> tn(px); std::vector<uint32_t> mesh(px); std::vector<float2> uv(c->sc.has_textures ? px : 0);
+    RCHECK(c, cudaMemcpy(tn.data(), (const float4*)c->gb_tn.p + off, px * sizeof(float4), cudaMemcpyDeviceToHost));
+    RCHECK(c, cudaMemcpy(mesh.data(), (const uint32_t*)c->gb_mesh.p + off, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (c->sc.has_textures) RCHECK(c, cudaMemcpy(uv.data(), (const float2*)c->gb_uv.p + off, px * sizeof(float2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < px; i++) {
+        size_t p = (size_t)c->y0 * c->W + i;
+        if (out->t) out->t[p] = tn[i].x;
+        if (out->normal) { out->normal[3 * p] = tn[i].y; out->normal[3 * p + 1] = tn[i].z; out->normal[3 * p + 2] = tn[i].w; }
+        if (out->mesh) out->mesh[p] = mesh[i];
+        if (out->texcoord) { out->texcoord[2 * p] = c->sc.has_textures ? uv[i].x : 0.0f; out->texcoord[2 * p + 1] = c->sc.has_textures ? uv[i].y : 0.0f; }
+    }
+    return ROMIS_OK;
+}
+
+extern "C" int romis_trace_rays(romis_ctx* c, const float* origins, const float* dirs, const float* tfar, int n, int any_hit,
+                                uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "romis_trace_rays: no scene");
+    if (n < 0 || (n > 0 && (!origins || !dirs || !tfar || !hit))) return fail(c, ROMIS_ERR_INVALID, "romis_trace_rays: bad arguments");
+    if (n == 0) return ROMIS_OK;
+    RCHECK(c, cudaSetDevice(c->device));
+    DevBuf d_o, d_d, d_tf, d_hit, d_t, d_u, d_v, d_tri;
+    int rc = ROMIS_OK;
+    auto done = [&](int code) { for (DevBuf* b : {&d_o, &d_d, &d_tf, &d_hit, &d_t, &d_u, &d_v, &d_tri}) b->release(); return code; };
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(d_o.ensure((size_t)n * 12)); ok(d_d.ensure((size_t)n * 12)); ok(d_tf.ensure((size_t)n * 4)); ok(d_hit.ensure((size_t)n));
+    ok(d_t.ensure((size_t)n * 4)); ok(d_u.ensure((size_t)n * 4)); ok(d_v.ensure((size_t)n * 4)); ok(d_tri.ensure((size_t)n * 4));
+    if (e == cudaSuccess) {
+        ok(cudaMemcpyAsync(d_o.p, origins, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        ok(cudaMemcpyAsync(d_d.p, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        ok(cudaMemcpyAsync(d_tf.p, tfar, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        ok(cudaMemsetAsync(d_t.p, 0, (size_t)n * 4, c->stream)); ok(cudaMemsetAsync(d_u.p, 0, (size_t)n * 4, c->stream));
+        ok(cudaMemsetAsync(d_v.p, 0, (size_t)n * 4, c->stream)); ok(cudaMemsetAsync(d_tri.p, 0xff, (size_t)n * 4, c->stream));
+        launch_trace(c->stream, n, c->sc, (const float*)d_o.p, (const float*)d_d.p, (const float*)d_tf.p, any_hit,
+                     (uint8_t*)d_hit.p, (float*)d_t.p, (float*)d_u.p, (float*)d_v.p, (uint32_t*)d_tri.p);
+        ok(cudaGetLastError());
+        ok(cudaMemcpyAsync(hit, d_hit.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        if (t) ok(cudaMemcpyAsync(t, d_t.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (u) ok(cudaMemcpyAsync(u, d_u.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (v) ok(cudaMemcpyAsync(v, d_v.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (tri) ok(cudaMemcpyAsync(tri, d_tri.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        ok(cudaStreamSynchronize(c->stream));
+    }
+    if (e != cudaSuccess) rc = fail(c, ROMIS_ERR_CUDA, std::string("romis_trace_rays: ") + cudaGetErrorString(e));
+    return done(rc);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" void* romis_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void romis_host_free(void* p) { if (p) cudaFreeHost(p); }

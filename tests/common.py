@@ -1,0 +1,63 @@
+"""Helpers shared by the parity tests."""
+import os
+
+import numpy as np
+
+from romis_b200 import abi
+from romis_b200.scene import Scene
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+def load_scene(name: str) -> Scene:
+    return Scene.load(os.path.join(GOLDEN, "scenes", name + ".npz"))
+
+
+def load_golden(case: str):
+    return np.load(os.path.join(GOLDEN, case + ".npz"))
+
+
+def camera_from_array(a) -> abi.romis_camera:
+    c = abi.romis_camera()
+    c.origin = abi.f3(*[float(x) for x in a[0:3]]); c.quat = abi.f4(*[float(x) for x in a[3:7]])
+    c.half_width = float(a[7]); c.half_height = float(a[8])
+    return c
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def assert_bits_equal(a, b, what):
+    """Bit-exact comparison (NaN-safe, distinguishes -0 from +0)."""
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    ba, bb = bits(a), bits(b)
+    if not np.array_equal(ba, bb):
+        bad = np.argwhere(ba != bb)
+        i = tuple(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} of {ba.size} elements differ; first at {i}: {a[i]!r} vs {b[i]!r}")
+
+
+def assert_rel_close(a, b, rel, what):
+    """|a - b| <= rel * max(|a|, |b|) element-wise (north_star: weights and radiance within 1e-4 relative)."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, f"{what}: shape"
+    tol = rel * np.maximum(np.abs(a), np.abs(b))
+    bad = ~(np.abs(a - b) <= tol)
+    bad &= ~(np.isnan(a) & np.isnan(b))
+    if bad.any():
+        i = tuple(np.argwhere(bad)[0])
+        raise AssertionError(f"{what}: {bad.sum()} of {a.size} beyond rel {rel}; first at {i}: {a[i]!r} vs {b[i]!r}")
+
+
+def stage_ids(features, frame):
+    ids = [abi.ROMIS_PASS_INITIAL]
+    if features.temporalReuse and frame > 0:
+        ids.append(abi.ROMIS_PASS_TEMPORAL)
+    if features.spatialReuse:
+        ids += [abi.ROMIS_PASS_SPATIAL0 + p for p in range(min(8, features.spatialResamplingPasses))]
+    ids.append(abi.ROMIS_PASS_FINAL)
+    return ids

@@ -1,0 +1,25 @@
+"""Golden cases shared by the generator (gen_golden.py, needs /root/reference) and the tests."""
+from romis_b200.scene import Camera, Features
+
+NIGHTCLUB_CAM = Camera()                                            # reference src/utils/config.h:21-26
+CORNELL_CAM = Camera(50.0, 3.0, (0.0, 0.0, 0.0), (20.0, 20.0, 0.0))   # TOML fallback camera, src/utils/config.cpp:249-252
+
+# name -> (scene, W, H, Features, Camera, frames, seed)
+CASES = {
+    "nightclub_default": ("CornellNightClub", 48, 32, Features(), NIGHTCLUB_CAM, 2, 7),
+    "nightclub_c2": ("CornellNightClub", 40, 30, Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), NIGHTCLUB_CAM, 3, 11),
+    "nightclub_unbiased_vis_n1": ("CornellNightClub", 32, 32, Features(unbiasedCombination=True, spatialReuseVisibilityCheck=True,
+                                                                        numSamplesInReservoir=1), NIGHTCLUB_CAM, 2, 13),
+    "nightclub_unbiased_n3": ("CornellNightClub", 32, 24, Features(unbiasedCombination=True, numSamplesInReservoir=3,
+                                                                    numNeighboursToSample=3, spatialResampleRadius=4), NIGHTCLUB_CAM, 2, 17),
+    "nightclub_n5_generic": ("CornellNightClub", 24, 24, Features(numSamplesInReservoir=5, initialLightSamples=16, temporalClampM=2), NIGHTCLUB_CAM, 3, 19),
+    "cornell_c1": ("CornellBoxParallelogramLight", 48, 48, Features(spatialResamplingPasses=1), CORNELL_CAM, 2, 23),
+    "cornell_point_n1": ("CornellBox", 40, 40, Features(spatialResamplingPasses=1, numSamplesInReservoir=1), CORNELL_CAM, 2, 29),
+    "monkey": ("Monkey", 40, 40, Features(), CORNELL_CAM, 2, 31),
+    "cube_segment": ("Cube", 32, 32, Features(numSamplesInReservoir=4, gamma=2.2, exposure=0.8), CORNELL_CAM, 2, 37),
+    "cube_textured": ("CubeTextured", 32, 32, Features(), CORNELL_CAM, 2, 41),
+    "triangle_noshading_k0": ("SingleTriangle", 24, 24, Features(enableShading=False, numNeighboursToSample=0, enableToneMapping=False), CORNELL_CAM, 2, 43),
+    "nightclub_no_spatial": ("CornellNightClub", 32, 24, Features(spatialReuse=False), NIGHTCLUB_CAM, 3, 47),
+    "nightclub_no_temporal": ("CornellNightClub", 32, 24, Features(temporalReuse=False, spatialResampleRadius=30, numNeighboursToSample=10), NIGHTCLUB_CAM, 2, 53),
+}
+SCENES = ["SingleTriangle", "Cube", "CubeTextured", "CornellBox", "CornellBoxParallelogramLight", "CornellNightClub", "Monkey"]

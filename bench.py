@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py -- the ReSTIR frame benchmark (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4k]
+
+A "step" is one ReSTIR frame (renderReSTIR, reference src/rendering/render.cpp:28-62) of the workload:
+  c2 (default)  cornell-nightclub, 1920x1080, M=32, N=2, temporal + 3 spatial passes k=5 r=10, visibility reuse
+                (BASELINE.json configs[1], the configuration the metric is quoted on)
+Frame 0 has no temporal history, so warm-up frames establish it; every timed frame runs all seven passes.
+
+  value  frames/s with everything resident in HBM, device time (CUDA events on the launching stream), image left
+         on the device.  For N > 1 the frame is split into N row bands, one process per GPU, reservoir halo rows
+         exchanged over NCCL before each spatial pass; time = max over ranks; "scaling": "strong" (one frame).
+  e2e    the same metric through the reference-facing call romis_render_frame with HOST buffers: per step the
+         scene's lights are re-uploaded (the reference reads scene.lights fresh every frame, light.cpp:46-66) and
+         the float RGB image is read back into pinned host memory, both inside the timed region.
+  roofline / cpu_baseline: see DESIGN.md "measurement".
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/libromis_ref.so: the reference's
+translation units compiled here, OpenMP on all host cores, thread-safe RNG shim) on a bounded sample of the same
+workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from romis_b200.scene import Camera, Features, Scene, synthetic_lights  # noqa: E402
+
+SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
+SEED = 20240229
+
+
+def workload(name: str):
+    """-> (label, scene, W, H, Features, Camera)."""
+    if name == "c1":
+        s = Scene.load(os.path.join(SCENES, "CornellBoxParallelogramLight.npz"))
+        return ("CornellBox-Mirror-Rotated 512x512 M=32 N=2 temporal + 1 spatial k=5 r=10", s, 512, 512,
+                Features(spatialResamplingPasses=1), Camera(50.0, 3.0, (0.0, 0.0, 0.0), (20.0, 20.0, 0.0)))
+    if name == "c2":
+        s = Scene.load(os.path.join(SCENES, "CornellNightClub.npz"))
+        return ("cornell-nightclub 1920x1080 M=32 N=2 temporal + 3 spatial k=5 r=10, visibility reuse", s, 1920, 1080,
+                Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), Camera())
+    if name == "c3":
+        s = Scene.load(os.path.join(SCENES, "Monkey.npz"))
+        s.lights = synthetic_lights(65536, seed=1)
+        return ("monkey + 65536 synthetic point/parallelogram lights 3840x2160 M=32 N=2 temporal + 3 spatial k=5 r=10", s, 3840, 2160,
+                Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), Camera(50.0, 3.0, (0.0, 0.0, 0.0), (20.0, 20.0, 0.0)))
+    if name == "c4k":
+        s = Scene.load(os.path.join(SCENES, "CornellNightClub.npz"))
+        return ("cornell-nightclub 3840x2160 M=32 N=2 temporal + 3 spatial k=5 r=10, visibility reuse", s, 3840, 2160,
+                Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), Camera())
+    raise SystemExit(f"unknown config {name}")
+
+
+# algorithmic bytes per pixel per pass: S = 20 B per sub-reservoir, G = 20 B per pixel
+def pass_bytes(N: int):
+    return {"primary": 20, "initial": 20 + 20 * N, "temporal": 20 + 60 * N, "spatial": 20 + 40 * N, "shade": 32 + 20 * N}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []; self.proc = None; self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = []; mx = 0; reasons = set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, label, scene, W, H, feat, cam, rank, world):
+    """The reference's own CPU path on the host cores, bounded sample = the workload at 1/4 x 1/4 resolution."""
+    if rank != 0:
+        return
+    from oracle.pyoracle import RefLib, REF_FLAG_TIMING_RNG
+    ref = RefLib()
+    ref.set_scene(scene)
+    div = 4 if W * H >= 1920 * 1080 else 2
+    w, h = W // div, H // div
+    scale = (w * h) / float(W * H)
+    times = []
+    for fr in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref.render_frame(feat, cam, w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+        dt = time.perf_counter() - t0
+        if fr >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times)) / scale          # scaled to the full frame: cost is linear in pixels
+    fps = 1e3 / ms
+    cores = ref.num_threads()
+    sample = f"{w}x{h} frames of the same scene/Features ({scale:.4f} of the pixels), time scaled by pixel count; OpenMP {cores} threads, thread-safe RNG shim"
+    line = {"impl": "reference", "metric": "ReSTIR frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": label, "width": W, "height": H},
+            "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(scene, W, H, feat, cam, budget_s=20.0):
+    """Reported baseline next to the GPU number: oracle/_ref (the compiled reference) when present, else the C port."""
+    div = 4 if W * H >= 1920 * 1080 else 2
+    w, h = W // div, H // div
+    scale = (w * h) / float(W * H)
+    try:
+        from oracle.pyoracle import RefLib, REF_FLAG_TIMING_RNG
+        ref = RefLib(); ref.set_scene(scene)
+        kind, cores = "reference", ref.num_threads()
+
+        def frame(fr):
+            ref.render_frame(feat, cam, w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+    except (FileNotFoundError, OSError):
+        from oracle.pyoracle import Oracle
+        orc = Oracle(); orc.upload_scene(scene)
+        kind, cores = "port", os.cpu_count() or 1
+        cam_abi = cam.to_abi(w, h)
+
+        def frame(fr):
+            orc.render_frame(feat, cam_abi, w, h, fr > 0, SEED, fr)
+    frame(0)
+    times = []; t_start = time.perf_counter(); fr = 1
+    while len(times) < 5 and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter(); frame(fr); times.append(time.perf_counter() - t0); fr += 1
+    ms = 1e3 * float(np.median(times)) / scale
+    return {"value": 1e3 / ms, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": f"{len(times)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    label, scene, W, H, feat, cam = workload(args.config)
+
+    if args.impl == "reference":
+        run_reference(args, label, scene, W, H, feat, cam, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from romis_b200.api import PinnedImage, RestirRenderer
+    from romis_b200.bands import BandedRenderer, band_rows
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    r = RestirRenderer(local_rank)
+    r.upload_scene(scene)
+    br = BandedRenderer(r, rank, world, device)
+    N = feat.numSamplesInReservoir
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def run_steps(n_steps, first_frame, host_out=None, upload_lights=False, stage_timing=False):
+        """Returns (sum of per-step device ms, per-stage sums).  L2 is flushed before every step, outside the events."""
+        r.set_stage_timing(stage_timing)
+        total = 0.0; stages = {}
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        for i in range(n_steps):
+            fr = first_frame + i
+            with torch.cuda.stream(br.stream):
+                flush.fill_(i & 0xff)
+                ev0.record(br.stream)
+            if upload_lights:
+                r.upload_lights(scene.lights)
+            br.render_frame(feat, cam, W, H, fr > 0, SEED, fr, out=host_out)
+            with torch.cuda.stream(br.stream):
+                ev1.record(br.stream)
+            ev1.synchronize()
+            total += ev0.elapsed_time(ev1)
+            if stage_timing:
+                t = r.timings()
+                for k in ("primary_ms", "initial_ms", "temporal_ms", "shade_ms"):
+                    stages[k] = stages.get(k, 0.0) + getattr(t, k)
+                stages["spatial_ms"] = stages.get("spatial_ms", 0.0) + sum(t.spatial_ms[:t.n_spatial])
+                stages["n_spatial"] = t.n_spatial
+                stages["launches"] = t.n_launches
+        return total, stages
+
+    # ---- warm-up (establishes temporal history), then the timed K steps: device-resident ----
+    run_steps(args.warmup, 0)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier(); wall0 = time.perf_counter()
+    dev_ms, _ = run_steps(args.steps, args.warmup)
+    barrier(); wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches_per_frame = r.timings().n_launches
+
+    # ---- per-stage times of the same steps (stage events split the frame; not used for `value`) ----
+    stage_ms, stages = run_steps(args.steps, args.warmup + args.steps, stage_timing=True)
+
+    # ---- e2e: host buffers through romis_render_frame semantics ----
+    pinned = PinnedImage(H, W)
+    run_steps(2, args.warmup + 2 * args.steps, host_out=pinned.array, upload_lights=True)
+    barrier()
+    e2e_ms, _ = run_steps(args.steps, args.warmup + 2 * args.steps + 2, host_out=pinned.array, upload_lights=True)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None      # sampled over the timed region and the two repeat legs (same workload)
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms, stage_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, stage_ms = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    fps = 1e3 / ms_per_step
+    e2e_fps = 1e3 / (e2e_ms / args.steps)
+    y0, y1 = band_rows(H, world, rank)
+    px = (y1 - y0) * W
+    peak, peak_src = measured_peak_gbs()
+    pb = pass_bytes(N)
+    per_pass = {}
+    for name, key, cnt in (("primary", "primary_ms", 1), ("initial", "initial_ms", 1), ("temporal", "temporal_ms", 1),
+                           ("spatial", "spatial_ms", max(1, stages.get("n_spatial", 1))), ("shade", "shade_ms", 1)):
+        ms = stages.get(key, 0.0) / args.steps / cnt
+        if ms > 0:
+            gbs = pb[name] * px / (ms * 1e-3) / 1e9
+            per_pass[name] = {"ms_per_launch": round(ms, 4), "algorithmic_bytes_per_px": pb[name], "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    dominant = max(per_pass, key=lambda k: per_pass[k]["ms_per_launch"] * (stages.get("n_spatial", 1) if k == "spatial" else 1))
+    roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": per_pass[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_pass[dominant]["frac"], "traffic": None, "peak_source": peak_src,
+                "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the pass kernels are issue-bound by the parity-exact fp32/fp64 arithmetic, see DESIGN.md",
+                "passes": per_pass}
+    line = {"metric": "ReSTIR frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the step's events)",
+                       "sharding": f"{world} row band(s), halo = radius rows over NCCL p2p" if world > 1 else "single GPU"},
+            "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
+            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(scene.lights.nbytes + 128),
+                    "d2h_bytes_per_step": int(px * 12), "gcandidates_per_s": W * H * feat.initialLightSamples * e2e_fps / 1e9},
+            "gpu_launches": int(launches_per_frame * args.steps),
+            "clocks": clk, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(scene, W, H, feat, cam)
+    print(json.dumps(line), flush=True)
+    pinned.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

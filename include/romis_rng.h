@@ -66,10 +66,15 @@ ROMIS_RNG_HD romis_stream_key romis_rng_stream(uint64_t seed, uint32_t frame, ui
     return k;
 }
 
-/* The counter-th 32-bit draw of a stream. */
+/* The counter-th 32-bit draw of a stream: one finaliser over k0 + counter * golden, with the second key
+ * word folded in between its two multiply rounds. */
 ROMIS_RNG_HD uint32_t romis_rng_bits(romis_stream_key k, uint32_t counter) {
-    uint32_t x = romis_mix32(k.k0 + counter * 0x9e3779b1u);
-    return romis_mix32(x ^ k.k1);
+    uint32_t x = k.k0 + counter * 0x9e3779b1u;
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= k.k1;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
 }
 
 /* rand() replacement: [0, 2^31 - 1] */

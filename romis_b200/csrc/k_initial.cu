@@ -8,7 +8,7 @@ namespace romis {
 // initial RIS: M candidates per pixel, + visibility reuse
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.y1) return;
@@ -18,6 +18,14 @@ __global__ void __launch_bounds__(256) initial_kernel(SceneDev sc, FrameDev fr, 
     SubRes<NT> r; res_init(r, N);
     if (sc.n_lights == 0) { res_store(out, y - fr.ey0, x, r, N); return; }          // light.cpp:46: M_j stays 1
     PixCtx c = make_ctx(sc, fr, g, x, y);
+    if (c.miss) {
+        // every candidate weighs p^ / (1/L) = 0: wSums never leave FLT_MIN, so sub-reservoir 0 wins every strict-'<'
+        // argmin (reservoir.cpp:12-19) and takes all M updates, nothing is ever accepted, W = 0
+        ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;
+        r.M[0] = fr.f.initialLightSamples;
+        res_store(out, y - fr.ey0, x, r, N);
+        return;
+    }
     romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_ENGINE);
     romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, 
 // final shading + tone mapping -> Screen layout (row-flipped float RGB)
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.y1) return;
@@ -46,8 +46,11 @@ __global__ void __launch_bounds__(256) shade_kernel(SceneDev sc, FrameDev fr, GB
     const int lrow = y - fr.ey0;
     PixCtx c = make_ctx(sc, fr, g, x, y);
     v3 color = V3(0, 0, 0);
-    for (int j = 0; j < N; j++) {                                                   // render_utils.cpp:56-62
+    // Miss pixels shade to exactly +0 (computeShading is 0, W is 0); a sample with W == 0 adds (+-0) and leaves the sum
+    // unchanged whatever its visibility: both skip the shadow ray and the shading without changing a bit.
+    for (int j = 0; j < N && !c.miss; j++) {                                        // render_utils.cpp:56-62
         uint4 rec = res_rec(in, lrow, j)[x];
+        if (__uint_as_float(rec.w) == 0.0f) continue;
         v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
         v3 scol = visible(sc, c, pos) ? compute_shading(c, es, pos, col) : V3(0, 0, 0);
         scol = scale3(scol, __uint_as_float(rec.w));

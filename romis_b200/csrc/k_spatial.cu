@@ -8,7 +8,7 @@ namespace romis {
 // spatial reuse, one pass: k neighbours from a (2r+1)^2 window of the previous iteration, self last
 // ------------------------------------------------------------------------------------------------
 template <int NT, bool UNBIASED>
-__global__ void __launch_bounds__(256) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.y1) return;
@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) spatial_kernel(SceneDev sc, FrameDev fr, 
                         ROMIS_FOR_SUB(j, NT, N) tot += res_m(in, srow, j)[sx];
                         ROMIS_FOR_SUB(j, NT, N) {
                 float pdf = target_pdf(cs, es, spos[j], scol[j]);
-                if (fr.f.spatialReuseVisibilityCheck) pdf *= visible(sc, cs, spos[j]) ? 1.0f : 0.0f;
-                if (pdf > 0.0f) Z[j] += tot;
+                // reservoir.cpp:89-92: pdf *= visibility; pdf > 0 counts.  The ray only matters when pdf > 0.
+                if (pdf > 0.0f && (!fr.f.spatialReuseVisibilityCheck || visible(sc, cs, spos[j]))) Z[j] += tot;
             }
         }
                 ROMIS_FOR_SUB(j, NT, N) {

@@ -8,7 +8,7 @@ namespace romis {
 // temporal reuse: same-pixel predecessor, M clamp, biased combine of {current, predecessor}
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.y1) return;

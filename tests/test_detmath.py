@@ -1,0 +1,68 @@
+"""Shared deterministic math (include/romis_detmath.h) and the counter-based RNG (include/romis_rng.h)."""
+import math
+
+import numpy as np
+
+from oracle.pyoracle import Oracle
+
+
+def ulp_diff(a: np.float32, b: np.float32) -> int:
+    if np.isnan(a) and np.isnan(b):
+        return 0
+    if a == b:
+        return 0
+    ia, ib = int(np.float32(a).view(np.int32)), int(np.float32(b).view(np.int32))
+    if (ia < 0) != (ib < 0):
+        return 1 << 30
+    return abs(ia - ib)
+
+
+def test_powf_expf_within_one_ulp_of_libm():
+    orc = Oracle()
+    rng = np.random.default_rng(0)
+    worst = 0
+    for _ in range(20000):
+        x = np.float32(rng.uniform(0, 2)); y = np.float32(rng.uniform(0, 300))
+        if rng.random() < 0.3:
+            y = np.float32(rng.integers(0, 300))          # integer exponents take the squaring path
+        ref = np.float32(math.pow(float(x), float(y))) if x > 0 else np.float32(0.0 if y > 0 else 1.0)
+        worst = max(worst, ulp_diff(np.float32(orc.lib.orc_powf(float(x), float(y))), ref))
+    assert worst <= 1
+    worst = 0
+    for _ in range(20000):
+        x = np.float32(rng.uniform(-80, 80))
+        worst = max(worst, ulp_diff(np.float32(orc.lib.orc_expf(float(x))), np.float32(math.exp(float(x)))))
+    assert worst <= 1
+    orc.close()
+
+
+def test_powf_special_cases_follow_c99():
+    orc = Oracle()
+    p = lambda x, y: np.float32(orc.lib.orc_powf(x, y))
+    inf, nan = float("inf"), float("nan")
+    assert p(nan, 0.0) == 1 and p(1.0, nan) == 1 and np.isnan(p(nan, 2.0)) and np.isnan(p(2.0, nan))
+    assert np.isnan(p(-0.5, 0.5))                         # negative base, non-integer exponent
+    assert p(-0.5, 3.0) == np.float32(-0.125) and p(-0.5, 2.0) == np.float32(0.25)
+    assert p(0.0, -1.0) == inf and p(-0.0, -1.0) == -inf and p(0.0, 2.0) == 0
+    assert p(2.0, inf) == inf and p(0.5, inf) == 0 and p(-1.0, inf) == 1
+    assert p(inf, -1.0) == 0 and p(-inf, 3.0) == -inf
+    assert p(10.0, 39.0) == inf and p(0.1, 50.0) == 0 and p(0.99, 250.0) == np.float32(math.pow(np.float32(0.99), 250.0))
+    assert np.float32(orc.lib.orc_expf(-inf)) == 0 and np.float32(orc.lib.orc_expf(inf)) == inf and np.float32(orc.lib.orc_expf(0.0)) == 1
+    orc.close()
+
+
+def test_rng_streams_are_uniform_and_keyed():
+    orc = Oracle()
+    bits = np.array([orc.lib.orc_rng_bits(99, 3, 2, 1234, 1, c) for c in range(20000)], np.uint64)
+    u = (bits >> np.uint64(1)).astype(np.float64) / 2147483648.0
+    assert 0.49 < u.mean() < 0.51 and 0.32 < (u < 1 / 3).mean() < 0.345
+    assert len(np.unique(bits)) > 19990
+    other = np.array([orc.lib.orc_rng_bits(99, 3, 2, 1235, 1, c) for c in range(2000)], np.uint64)
+    assert (other == bits[:2000]).sum() == 0                # neighbouring pixels: unrelated streams
+    again = np.array([orc.lib.orc_rng_bits(99, 3, 2, 1234, 1, c) for c in range(100)], np.uint64)
+    assert np.array_equal(again, bits[:100])                # addressable without state
+    # multiply-shift mapping of uniform_int_distribution(-r, r) covers the window evenly
+    r = 10
+    d = -r + ((bits.astype(np.uint64) * np.uint64(2 * r + 1)) >> np.uint64(32)).astype(np.int64)
+    assert d.min() == -r and d.max() == r and np.bincount(d + r).min() > 20000 / 21 * 0.8
+    orc.close()

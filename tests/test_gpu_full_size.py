@@ -1,0 +1,61 @@
+"""CUDA path at BASELINE.json's full size (configs[1]: nightclub 1920x1080, M=32, temporal + 3 spatial, visibility reuse):
+size-independent properties (the oracle cannot run this size in seconds) + bit-exact agreement with the oracle on a
+sub-window of rows rendered as a band."""
+import numpy as np
+import pytest
+
+from romis_b200 import abi
+from romis_b200.scene import Features
+from cases import NIGHTCLUB_CAM
+from common import assert_bits_equal, load_scene
+from test_oracle_properties import check_frame_invariants
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_size_invariants_determinism_and_band_equivalence():
+    from romis_b200.api import RestirRenderer
+    scene = load_scene("CornellNightClub")
+    feat = Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True)
+    W, H = 1920, 1080
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    imgs = []
+    for run in range(2):
+        r = RestirRenderer(0); r.upload_scene(scene); r.set_capture(run == 0)
+        prev = None
+        for fr in range(2):
+            img = r.render_frame(feat, cam, W, H, fr > 0, 2024, fr)
+            if run == 0:
+                ids = [abi.ROMIS_PASS_INITIAL] + ([abi.ROMIS_PASS_TEMPORAL] if fr else []) + \
+                      [abi.ROMIS_PASS_SPATIAL0 + p for p in range(3)] + [abi.ROMIS_PASS_FINAL]
+                prev = check_frame_invariants(r.gbuffer(), {i: r.reservoirs(i) for i in ids}, feat, len(scene.lights), prev)
+                assert np.isfinite(img).all() and (img >= 0).all() and (img <= 1).all()
+        imgs.append(img)
+        r.close()
+    assert_bits_equal(imgs[0], imgs[1], "two runs, same seed")
+    # a 3-band split of the same frame (halos copied on the device) reproduces the full frame bit for bit
+    import ctypes as C
+    cudart = C.CDLL("libcudart.so")
+    bands = [RestirRenderer(0) for _ in range(3)]
+    edges = [0, 333, 700, H]
+    for i, b in enumerate(bands):
+        b.set_band(edges[i], edges[i + 1]); b.upload_scene(scene)
+    img = np.zeros((H, W, 3), np.float32)
+    for fr in range(2):
+        for b in bands:
+            b.frame_begin(feat, cam, W, H, fr > 0, 2024, fr)
+        for p in range(3):
+            for b in bands:
+                b.synchronize()
+            for i in range(2):
+                s, n = bands[i].halo_region(abi.ROMIS_HALO_SEND_HIGH); d, m = bands[i + 1].halo_region(abi.ROMIS_HALO_RECV_LOW)
+                assert n == m > 0 and cudart.cudaMemcpy(C.c_void_p(d), C.c_void_p(s), C.c_size_t(n), 3) == 0
+                s, n = bands[i + 1].halo_region(abi.ROMIS_HALO_SEND_LOW); d, m = bands[i].halo_region(abi.ROMIS_HALO_RECV_HIGH)
+                assert n == m > 0 and cudart.cudaMemcpy(C.c_void_p(d), C.c_void_p(s), C.c_size_t(n), 3) == 0
+            for b in bands:
+                b.frame_spatial_pass(p)
+        for b in bands:
+            b.frame_end(img)
+    assert_bits_equal(img, imgs[0], "3 row bands vs single context at 1080p")
+    for b in bands:
+        b.close()

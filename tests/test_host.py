@@ -1,0 +1,69 @@
+"""Host-side logic: parameter / camera / scene marshalling, row-band partitioning, synthetic lights."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from romis_b200 import abi
+from romis_b200.bands import band_rows, check_bands
+from romis_b200.scene import Camera, Features, LIGHT_DTYPE, Scene, synthetic_lights
+from cases import CASES
+from common import load_golden, load_scene
+
+
+def test_features_defaults_mirror_reference():
+    f = Features()                               # reference src/utils/common.h:103-136
+    assert (f.numSamplesInReservoir, f.initialLightSamples, f.numNeighboursToSample, f.spatialResampleRadius) == (2, 32, 5, 10)
+    assert (f.spatialResamplingPasses, f.temporalClampM, f.gamma, f.exposure) == (2, 20, 1.0, 1.5)
+    assert f.enableShading and f.spatialReuse and f.temporalReuse and f.enableToneMapping
+    assert not (f.unbiasedCombination or f.spatialReuseVisibilityCheck or f.initialSamplesVisibilityCheck)
+    a = f.to_abi()
+    assert a.initialLightSamples == 32 and a.exposure == 1.5 and a.unbiasedCombination == 0
+
+
+@pytest.mark.parametrize("case", ["nightclub_default", "cornell_c1"])
+def test_camera_marshalling_matches_reference_trackball(case):
+    """Camera.to_abi restates Trackball::position / glm::quat(euler) (trackball.cpp:75-78, type_quat.inl:208-217); the golden
+    camera was computed by the reference's own Trackball.  numpy's sin/cos may differ from glibc's in the last bit."""
+    _s, W, H, _f, cam, _n, _seed = CASES[case]
+    ref = load_golden(case)["camera"]
+    c = cam.to_abi(W, H)
+    mine = np.array([*c.origin, *c.quat, c.half_width, c.half_height], np.float32)
+    assert np.allclose(mine, ref, rtol=2e-6, atol=2e-6)
+
+
+def test_scene_roundtrip_and_fixture_contents():
+    s = load_scene("CornellNightClub")
+    assert len(s.meshes) == 18 and s.n_triangles == 166 and len(s.lights) == 512
+    assert (s.lights["type"] == abi.ROMIS_LIGHT_PARALLELOGRAM).all()
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "s.npz"); s.save(p); t = Scene.load(p)
+    assert len(t.meshes) == 18 and np.array_equal(t.lights, s.lights)
+    assert all(np.array_equal(a.vertices, b.vertices) and np.array_equal(a.triangles, b.triangles) for a, b in zip(s.meshes, t.meshes))
+    assert load_scene("Monkey").n_triangles == 968 and len(load_scene("CubeTextured").textures) == 1
+    descs, nm, texs, nt, keep = s.to_abi()
+    assert nm == 18 and descs[0].n_triangles == len(s.meshes[0].triangles) and descs[3].material.shininess == 250.0
+
+
+def test_synthetic_lights_are_seed_fixed():
+    a, b = synthetic_lights(1000, seed=4), synthetic_lights(1000, seed=4)
+    assert a.dtype == LIGHT_DTYPE and np.array_equal(a, b)
+    assert not np.array_equal(a, synthetic_lights(1000, seed=5))
+    r = np.linalg.norm(a["p0"], axis=1)
+    assert (r >= 1.49).all() and (r <= 3.01).all()
+    assert (a["type"] == abi.ROMIS_LIGHT_POINT).sum() == 500
+    assert np.abs(a["e1"]).max() <= 0.05
+
+
+def test_band_partition():
+    for H in (1, 7, 1080, 2160):
+        for G in (1, 2, 3, 4, 8):
+            rows = [band_rows(H, G, r) for r in range(G)]
+            assert rows[0][0] == 0 and rows[-1][1] == H
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(G - 1))
+            sizes = [b - a for a, b in rows]
+            assert max(sizes) - min(sizes) <= 1
+    check_bands(1080, 8, 30)
+    with pytest.raises(ValueError):
+        check_bands(64, 8, 10)

@@ -1,0 +1,170 @@
+// render_restir_gpu.cpp -- the reference-side host code of the drop-in: a replacement BODY for
+//
+//     ReservoirGrid renderReSTIR(std::shared_ptr<ReservoirGrid> previousFrameGrid, const Scene& scene,
+//                                const Trackball& camera, const EmbreeInterface& embreeInterface,
+//                                Screen& screen, const Features& features);      (reference src/rendering/render.h:25-28)
+//
+// written against the reference's OWN headers (Scene, Mesh, Trackball, Screen, Features, ReservoirGrid) and the C-ABI of
+// include/romis_gpu.h.  A maintainer drops this file into src/rendering/, removes the body of renderReSTIR from
+// render.cpp (lines 28-62) and links libromis_gpu.so; nothing else in the renderer, UI or scene loader changes
+// (INTEGRATION.md).  In this repo it is compiled by `make -C oracle dropin` into oracle/_ref/libromis_dropin.so together
+// with the reference's translation units, and tests/test_gpu_dropin.py checks that the reference's own Scene / Trackball
+// / Screen objects driven through it produce the reference's image bit for bit.
+//
+// Compile with -DROMIS_DROPIN_NAME=<symbol> to emit the function under another name (the test library keeps the
+// reference's CPU renderReSTIR next to it).
+#include <rendering/render.h>
+#include <rendering/reservoir.h>
+#include <rendering/screen.h>
+#include <scene/scene.h>
+#include <utils/common.h>
+#include <framework/trackball.h>
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "romis_gpu.h"
+
+#ifndef ROMIS_DROPIN_NAME
+#define ROMIS_DROPIN_NAME renderReSTIR
+#endif
+
+namespace {
+
+struct GpuState {
+    romis_ctx* ctx = nullptr;
+    const void* sceneKey = nullptr;     // identity of the uploaded geometry
+    size_t sceneSig = 0;
+    uint64_t seed = 0x524f4d4953ull;    // "ROMIS"
+    uint32_t frame = 0;
+    ~GpuState() { if (ctx) romis_destroy(ctx); }
+};
+// one context per calling thread: the reference's CLI mode renders one camera per std::thread (main.cpp:213-230)
+thread_local GpuState g;
+
+void check(int rc, const char* what) {
+    if (rc != ROMIS_OK) throw std::runtime_error(std::string(what) + ": " + romis_last_error(g.ctx));   // render.cpp:278 throws too
+}
+
+size_t geometrySignature(const Scene& scene) {
+    size_t h = scene.meshes.size();
+    for (const Mesh& m : scene.meshes) {
+        h = h * 1000003u + m.vertices.size(); h = h * 1000003u + m.triangles.size();
+        if (!m.vertices.empty()) { uint32_t b; std::memcpy(&b, &m.vertices[0].position.x, 4); h = h * 1000003u + b; }
+    }
+    return h;
+}
+
+void uploadScene(const Scene& scene) {
+    std::vector<romis_mesh_desc> descs(scene.meshes.size());
+    std::vector<std::vector<uint32_t>> tris(scene.meshes.size());
+    std::vector<const Image*> images;
+    std::vector<std::vector<float>> pixels;
+    std::vector<romis_texture> textures;
+    static_assert(sizeof(Vertex) == sizeof(romis_vertex), "Vertex {vec3 position, vec3 normal, vec2 texCoord} maps 1:1 (mesh.h:14-20)");
+    for (size_t i = 0; i < scene.meshes.size(); i++) {
+        const Mesh& m = scene.meshes[i];
+        for (const glm::uvec3& t : m.triangles) { tris[i].push_back(t.x); tris[i].push_back(t.y); tris[i].push_back(t.z); }
+        romis_mesh_desc& d = descs[i];
+        d.vertices = reinterpret_cast<const romis_vertex*>(m.vertices.data()); d.n_vertices = (uint32_t)m.vertices.size();
+        d.triangles = tris[i].data(); d.n_triangles = (uint32_t)m.triangles.size();
+        std::memcpy(d.material.kd, &m.material.kd.x, 12); std::memcpy(d.material.ks, &m.material.ks.x, 12);
+        d.material.shininess = m.material.shininess; d.material.transparency = m.material.transparency;
+        d.material.kd_texture = -1;
+        if (m.material.kdTexture) {
+            const Image* img = m.material.kdTexture.get();
+            size_t k = 0;
+            while (k < images.size() && images[k] != img) k++;
+            if (k == images.size()) {
+                images.push_back(img);
+                pixels.emplace_back(3 * img->pixels.size());
+                std::memcpy(pixels.back().data(), img->pixels.data(), 12 * img->pixels.size());
+            }
+            d.material.kd_texture = (int32_t)k;
+        }
+    }
+    for (size_t k = 0; k < images.size(); k++) textures.push_back(romis_texture { pixels[k].data(), images[k]->width, images[k]->height });
+    check(romis_upload_scene(g.ctx, descs.data(), (int)descs.size(), textures.data(), (int)textures.size()), "romis_upload_scene");
+}
+
+void uploadLights(const Scene& scene) {     // scene.lights is read fresh every frame by the reference (light.cpp:46-66)
+    std::vector<romis_light> lights(scene.lights.size());
+    for (size_t i = 0; i < scene.lights.size(); i++) {
+        romis_light l; std::memset(&l, 0, sizeof l);
+        const auto& v = scene.lights[i];
+        if (std::holds_alternative<PointLight>(v)) {
+            const PointLight& p = std::get<PointLight>(v); l.type = ROMIS_LIGHT_POINT;
+            std::memcpy(l.p0, &p.position.x, 12); std::memcpy(l.c0, &p.color.x, 12);
+        } else if (std::holds_alternative<SegmentLight>(v)) {
+            const SegmentLight& s = std::get<SegmentLight>(v); l.type = ROMIS_LIGHT_SEGMENT;
+            std::memcpy(l.p0, &s.endpoint0.x, 12); std::memcpy(l.e1, &s.endpoint1.x, 12);
+            std::memcpy(l.c0, &s.color0.x, 12); std::memcpy(l.c1, &s.color1.x, 12);
+        } else {
+            const ParallelogramLight& p = std::get<ParallelogramLight>(v); l.type = ROMIS_LIGHT_PARALLELOGRAM;
+            std::memcpy(l.p0, &p.v0.x, 12); std::memcpy(l.e1, &p.edge01.x, 12); std::memcpy(l.e2, &p.edge02.x, 12);
+            std::memcpy(l.c0, &p.color0.x, 12); std::memcpy(l.c1, &p.color1.x, 12);
+            std::memcpy(l.c2, &p.color2.x, 12); std::memcpy(l.c3, &p.color3.x, 12);
+        }
+        lights[i] = l;
+    }
+    check(romis_upload_lights(g.ctx, lights.data(), (int)lights.size()), "romis_upload_lights");
+}
+
+romis_features toPod(const Features& f) {
+    romis_features o;
+    o.enableShading = f.enableShading; o.enableTextureMapping = f.enableTextureMapping;
+    o.initialSamplesVisibilityCheck = f.initialSamplesVisibilityCheck;
+    o.numSamplesInReservoir = f.numSamplesInReservoir; o.initialLightSamples = f.initialLightSamples;
+    o.numNeighboursToSample = f.numNeighboursToSample; o.spatialResampleRadius = f.spatialResampleRadius;
+    o.unbiasedCombination = f.unbiasedCombination; o.spatialReuse = f.spatialReuse;
+    o.spatialReuseVisibilityCheck = f.spatialReuseVisibilityCheck; o.temporalReuse = f.temporalReuse;
+    o.spatialResamplingPasses = f.spatialResamplingPasses; o.temporalClampM = f.temporalClampM;
+    o.enableToneMapping = f.enableToneMapping; o.gamma = f.gamma; o.exposure = f.exposure;
+    return o;
+}
+
+}  // namespace
+
+// Random stream of the next frame (parity runs pin it; the interactive renderer can leave the defaults).
+extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame) { g.seed = seed; g.frame = frame; }
+
+// half extents of the image plane: Trackball keeps them private (trackball.h:55-56).  The maintainer either adds two
+// accessors or, as here, the caller provides them; they are tan(fovy/2) and aspect*tan(fovy/2) (trackball.cpp:26-27).
+static thread_local float g_halfW = 0.0f, g_halfH = 0.0f;
+extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight) { g_halfW = halfWidth; g_halfH = halfHeight; }
+
+ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid,
+                                const Scene& scene, const Trackball& camera,
+                                const EmbreeInterface& /*embreeInterface: the GPU path owns its own BVH*/, Screen& screen,
+                                const Features& features) {
+    if (!g.ctx) {
+        int dev = 0;
+        if (romis_create(&dev, 1, &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
+    }
+    // EmbreeInterface::changeScene (embree_interface.cpp:53-56) has no notification we could hook: detect geometry changes
+    const size_t sig = geometrySignature(scene);
+    if (g.sceneKey != scene.meshes.data() || g.sceneSig != sig) { uploadScene(scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; }
+    uploadLights(scene);
+
+    const glm::ivec2 res = screen.resolution();
+    romis_camera cam;
+    const glm::vec3 pos = camera.position();                                // trackball.cpp:75-78
+    const glm::quat q = glm::quat(camera.rotationEulerAngles());            // same expression generateRay uses (trackball.cpp:111)
+    cam.origin[0] = pos.x; cam.origin[1] = pos.y; cam.origin[2] = pos.z;
+    cam.quat[0] = q.w; cam.quat[1] = q.x; cam.quat[2] = q.y; cam.quat[3] = q.z;
+    cam.half_width = g_halfW; cam.half_height = g_halfH;
+    if (g_halfH == 0.0f) throw std::runtime_error("romis drop-in: image-plane half extents not set (romis_dropin_set_half_extents)");
+
+    const romis_features f = toPod(features);
+    romis_rng rng { g.seed, g.frame++, 0 };
+    // Screen::pixels() is the row-flipped float RGB framebuffer setPixel writes (screen.cpp:37-43,110-118)
+    float* out = &screen.pixels()[0].x;
+    check(romis_render_frame(g.ctx, &f, &cam, res.x, res.y, previousFrameGrid ? 1 : 0, &rng, out), "romis_render_frame");
+
+    // The reservoir grid lives on the device.  The caller only tests the returned grid for presence and hands a copy back
+    // next frame (main.cpp:165), so a 1x1 token is enough to carry "history exists".
+    return ReservoirGrid(1, std::vector<Reservoir>(1, Reservoir(features.numSamplesInReservoir)));
+}

@@ -22,6 +22,7 @@ from romis_b200.scene import Camera, Features, Scene, LIGHT_DTYPE, VERTEX_DTYPE,
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libromis_ref.so")
+DROPIN_SO = os.path.join(HERE, "_ref", "libromis_dropin.so")
 REFERENCE_ROOT = "/root/reference"
 
 
@@ -37,6 +38,9 @@ def build_ref() -> str | None:
     """Builds oracle/_ref when the reference tree is present; returns the path or None."""
     if os.path.isdir(REFERENCE_ROOT):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", "-j8"])
+        if os.path.exists(os.path.join(HERE, "..", "romis_b200", "libromis_gpu.so")):
+            # the reference's translation units + integration/render_restir_gpu.cpp on top of libromis_gpu.so
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin", "-j8"])
     return REF_SO if os.path.exists(REF_SO) else None
 
 
@@ -199,10 +203,10 @@ class RefFrame:
 class RefLib:
     """The compiled reference (oracle/_ref/libromis_ref.so).  Process-global state (one scene)."""
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(f"{REF_SO} not built (run `make -C oracle ref` where /root/reference exists)")
-        self.lib = C.CDLL(REF_SO)
+    def __init__(self, path: str = REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built (run `make -C oracle ref dropin` where /root/reference exists)")
+        self.lib = C.CDLL(path)
         L = self.lib
         L.ref_last_error.restype = C.c_char_p
         L.ref_render_frame.argtypes = [C.POINTER(abi.romis_features), C.POINTER(_ref_camera_desc), C.c_int, C.c_int, C.c_int,
@@ -306,3 +310,20 @@ class RefLib:
             for st in res.stages.values():
                 st.M = st.M64.astype(np.uint32)
         return res
+
+
+class DropinLib(RefLib):
+    """oracle/_ref/libromis_dropin.so: the reference's translation units plus integration/render_restir_gpu.cpp (the
+    replacement body of renderReSTIR) linked against libromis_gpu.so.  render_frame_gpu drives the reference's own Scene /
+    Trackball / Screen / Features objects through the GPU path."""
+
+    def __init__(self):
+        super().__init__(DROPIN_SO)
+        self.lib.ref_render_frame_dropin.argtypes = [C.POINTER(abi.romis_features), C.POINTER(_ref_camera_desc), C.c_int, C.c_int,
+                                                     C.c_int, C.POINTER(abi.romis_rng), C.c_void_p]
+
+    def render_frame_gpu(self, features: Features, camera: Camera, W: int, H: int, history_valid: bool, seed: int, frame: int):
+        f = features.to_abi(); r = abi.romis_rng(seed, frame, 0); cd = self._cam(camera)
+        img = np.zeros((H, W, 3), np.float32)
+        self._check(self.lib.ref_render_frame_dropin(C.byref(f), C.byref(cd), W, H, int(history_valid), C.byref(r), img.ctypes.data))
+        return img

@@ -234,6 +234,37 @@ int ref_make_camera(const ref_camera_desc* c, int width, int height, romis_camer
 }
 
 int ref_reset_history(void) { g_prev.reset(); return 0; }
+
+#ifdef ROMIS_WITH_DROPIN
+}  // extern "C"
+// integration/render_restir_gpu.cpp compiled with -DROMIS_DROPIN_NAME=renderReSTIR_gpu
+ReservoirGrid renderReSTIR_gpu(std::shared_ptr<ReservoirGrid> previousFrameGrid, const Scene& scene, const Trackball& camera,
+                               const EmbreeInterface& embreeInterface, Screen& screen, const Features& features);
+extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame);
+extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight);
+extern "C" {
+// The reference's own Scene / Trackball / Screen / Features objects driven through the GPU drop-in.
+int ref_render_frame_dropin(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
+                            const romis_rng* rng, float* out_rgb) {
+    if (!g_embree) { g_err = "no scene"; return -1; }
+    try {
+        const Features features = toFeatures(*f);
+        Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
+        Screen screen(glm::ivec2(W, H), false);
+        Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
+        camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
+        const float halfH = std::tan(glm::radians(cam->fov_deg) / 2.0f);            // trackball.cpp:26-27
+        romis_dropin_set_half_extents(window.getAspectRatio() * halfH, halfH);
+        romis_dropin_set_rng(rng->seed, rng->frame);
+        static std::shared_ptr<ReservoirGrid> prevGpu;
+        if (!history_valid) prevGpu.reset();
+        ReservoirGrid grid = renderReSTIR_gpu(prevGpu, g_scene, camera, *g_embree, screen, features);
+        prevGpu = std::make_shared<ReservoirGrid>(grid);                            // main.cpp:165
+        if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    return 0;
+}
+#endif
 int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         if (type != ROMIS_LIGHT_POINT) u = romis_rand_to_unit(romis_rng_rand(rk, rc++));        // light.cpp:20 / :28
         if (type == ROMIS_LIGHT_PARALLELOGRAM) v = romis_rand_to_unit(romis_rng_rand(rk, rc++)); // light.cpp:29
         v3 pos, col; light_sample(sc.lights, li, u, v, pos, col);
-        float w = target_pdf(c, es, pos, col) / invPdf;
+        float pdf = target_pdf(c, es, pos, col);
+        float w = 0.0f;                                     // +0 / (1/L) = +0: keep 0 / x off the slow division path
+        if (pdf != 0.0f) w = pdf / invPdf;
         res_update(r, N, li, u, v, w, rk, rc);
     }
     // light.cpp:85-95: visibility reuse zeroes W of occluded samples, otherwise W = (1/pdf)(1/M)wSum

@@ -32,7 +32,7 @@ template <int NT> struct SubRes {
 
 // Reservoir::Reservoir (reservoir.h:29-32)
 template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N) {
-        ROMIS_FOR_SUB(j, NT, N) {
+    ROMIS_FOR_SUB(j, NT, N) {
         r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull;
     }
 }
@@ -41,20 +41,28 @@ template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N)
 template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N, uint32_t light, float u, float v, float weight,
                                                             romis_stream_key rk, uint32_t& rc) {
     int idx = 0; float smallest = FLT_MAX;
-        ROMIS_FOR_SUB(j, NT, N) { if (r.wSum[j] < smallest) { idx = j; smallest = r.wSum[j]; } }
-    float rnd = romis_rand_to_unit(romis_rng_rand(rk, rc++));
-        ROMIS_FOR_SUB(j, NT, N) {
+    ROMIS_FOR_SUB(j, NT, N) { if (r.wSum[j] < smallest) { idx = j; smallest = r.wSum[j]; } }
+    // A weight of exactly 0 (light behind the surface, occluded or empty source sample) leaves wSum unchanged and makes
+    // the accept test `u < 0 / wSum` false for every u in [0, 1]: only the counters move.  Taking that case out also
+    // keeps 0 / x off nvcc's slow IEEE-division path (FCHK rejects a zero numerator).
+    const bool zero = weight == 0.0f;
+    const uint32_t draw = rc++;                                     // reservoir.cpp:24: one rand() per update, always
+    float rnd = 2.0f;
+    if (!zero) rnd = romis_rand_to_unit(romis_rng_rand(rk, draw));
+    ROMIS_FOR_SUB(j, NT, N) {                                       // predicated writes keep the arrays in registers
         if (j == idx) {
             r.M[j] += 1u;
-            r.wSum[j] += weight;
-            if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; }
+            if (!zero) {
+                r.wSum[j] += weight;
+                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; }
+            }
         }
     }
     return idx;
 }
 
 template <int NT> __device__ __forceinline__ void res_store(const ResBuf& b, int lrow, int x, const SubRes<NT>& r, int N) {
-        ROMIS_FOR_SUB(j, NT, N) {
+    ROMIS_FOR_SUB(j, NT, N) {
         res_rec(b, lrow, j)[x] = make_uint4(r.light[j], __float_as_uint(r.u[j]), __float_as_uint(r.v[j]), __float_as_uint(r.W[j]));
         res_m(b, lrow, j)[x] = r.M[j];
     }
@@ -62,10 +70,12 @@ template <int NT> __device__ __forceinline__ void res_store(const ResBuf& b, int
 
 // W_j = pdf == 0 ? 0 : (1/pdf) * (1/M_j) * wSum_j   (light.cpp:89-93, reservoir.cpp:57-65)
 template <int NT> __device__ __forceinline__ void res_finish(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es) {
-        ROMIS_FOR_SUB(j, NT, N) {
+    ROMIS_FOR_SUB(j, NT, N) {
         v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
         float pdf = target_pdf(c, es, pos, col);
-        r.W[j] = (pdf == 0.0f) ? 0.0f : (1.0f / pdf) * (1.0f / (float)r.M[j]) * r.wSum[j];
+        float Wj = 0.0f;
+        if (pdf != 0.0f) Wj = (1.0f / pdf) * (1.0f / (float)r.M[j]) * r.wSum[j];   // a real branch: 1/M with M = 0 stays unevaluated
+        r.W[j] = Wj;
     }
 }
 

@@ -52,6 +52,9 @@ def test_full_size_invariants_determinism_and_band_equivalence():
                 assert n == m > 0 and cudart.cudaMemcpy(C.c_void_p(d), C.c_void_p(s), C.c_size_t(n), 3) == 0
                 s, n = bands[i + 1].halo_region(abi.ROMIS_HALO_SEND_LOW); d, m = bands[i].halo_region(abi.ROMIS_HALO_RECV_HIGH)
                 assert n == m > 0 and cudart.cudaMemcpy(C.c_void_p(d), C.c_void_p(s), C.c_size_t(n), 3) == 0
+            # cudaMemcpy D2D returns before the copy has run and the contexts' non-blocking streams do not order against
+            # the legacy stream it uses: wait for the halos before launching the pass
+            assert cudart.cudaDeviceSynchronize() == 0
             for b in bands:
                 b.frame_spatial_pass(p)
         for b in bands:

@@ -160,6 +160,7 @@ def test_row_bands_reproduce_full_frame(oracle_factory):
                 assert s_n == r_n and s_n > 0
                 assert cudart.cudaMemcpy(C.c_void_p(r_ptr), C.c_void_p(s_ptr), C.c_size_t(s_n), 3) == 0
                 assert bands[0].halo_region(abi.ROMIS_HALO_SEND_LOW)[1] == 0 and bands[1].halo_region(abi.ROMIS_HALO_SEND_HIGH)[1] == 0
+                assert cudart.cudaDeviceSynchronize() == 0      # D2D cudaMemcpy is asynchronous w.r.t. the non-blocking context streams
                 for b in bands:
                     b.frame_spatial_pass(p)
             for b in bands:

@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-rows", action="store_true", help="N > 1: equal row counts instead of equal-cost bands")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -208,7 +210,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     r = RestirRenderer(local_rank)
     r.upload_scene(scene)
-    br = BandedRenderer(r, rank, world, device)
+    br = BandedRenderer(r, rank, world, device, transport=args.halo)
+    if world > 1 and not args.equal_rows:
+        br.balance(cam, W, H, feat.spatialResampleRadius if feat.spatialReuse else 0)
     N = feat.numSamplesInReservoir
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 
@@ -276,7 +280,7 @@ def main():
     ms_per_step = dev_ms / args.steps
     fps = 1e3 / ms_per_step
     e2e_fps = 1e3 / (e2e_ms / args.steps)
-    y0, y1 = band_rows(H, world, rank)
+    y0, y1 = br.band(H)
     px = (y1 - y0) * W
     peak, peak_src = measured_peak_gbs()
     pb = pass_bytes(N)
@@ -296,7 +300,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the step's events)",
-                       "sharding": f"{world} row band(s), halo = radius rows over NCCL p2p" if world > 1 else "single GPU"},
+                       "sharding": (f"{world} row bands, halo = radius rows, " + ("pushed into peer-mapped (CUDA IPC) buffers over NVLink, flag-ordered" if args.halo == "peer" else "NCCL p2p")) if world > 1 else "single GPU",
+                       "band_edges": br.edges if br.edges is not None else "equal rows"},
             "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(scene.lights.nbytes + 128),

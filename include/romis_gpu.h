@@ -154,6 +154,9 @@ int romis_synchronize(romis_ctx* ctx);
  * the output layout stay in global image coordinates, so N bands reproduce the 1-GPU frame bit for
  * bit.  Default (or y0 = y1 = 0): whole frame. */
 int romis_set_band(romis_ctx* ctx, int y0, int y1);
+/* Pixels per image row whose primary ray hits geometry (hits_per_row: height entries).  Work per pixel is concentrated in
+ * hit pixels, so hosts cut the frame into equal-COST bands with this profile; every rank computes the same numbers. */
+int romis_row_hit_counts(romis_ctx* ctx, const romis_camera* camera, int width, int height, uint32_t* hits_per_row);
 /* Stepwise frame for banded rendering: begin = primary (band + radius halo rows) + initial +
  * temporal; then per spatial pass: the caller moves halo rows between neighbouring bands
  * (romis_halo_region, any transport), calls romis_frame_spatial_pass; end = shade + read-back of the
@@ -169,6 +172,21 @@ enum { ROMIS_HALO_SEND_LOW = 0, ROMIS_HALO_SEND_HIGH = 1, ROMIS_HALO_RECV_LOW = 
 int romis_halo_region(romis_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
 /* CUDA stream (cudaStream_t) the context launches on, so the caller can order its transport. */
 int romis_stream(romis_ctx* ctx, void** cuda_stream);
+
+/* Peer-mapped halos (one process per GPU, all GPUs of one NVLink/NVSwitch node).  Instead of the caller moving halo rows,
+ * romis_frame_spatial_pass pushes this band's boundary rows straight into the neighbouring bands' halo rows (CUDA IPC
+ * mapped device memory) and orders the passes with flag words in device memory: no NCCL call, no host synchronisation.
+ *   1. every rank: romis_set_band, romis_upload_scene, romis_band_prepare (allocates the frame buffers now)
+ *   2. every rank: romis_peer_export -> ROMIS_PEER_BLOB_BYTES opaque bytes; exchange them out of band (any transport)
+ *   3. every rank: romis_peer_attach(blob of the band below or NULL, blob of the band above or NULL)
+ * All ranks must then issue the same sequence of frames.  A change of resolution / N / band needs a detach and a new
+ * prepare-export-attach round.  romis_peer_error reports whether a flag wait ever timed out (a neighbour died). */
+#define ROMIS_PEER_BLOB_BYTES 512
+int romis_band_prepare(romis_ctx* ctx, const romis_features* features, int width, int height);
+int romis_peer_export(romis_ctx* ctx, void* blob);
+int romis_peer_attach(romis_ctx* ctx, const void* low_blob, const void* high_blob);
+int romis_peer_detach(romis_ctx* ctx);
+int romis_peer_error(romis_ctx* ctx, int* timed_out);
 
 /* ---- parity / debug read-back (SURVEY.md 8b romis_download_reservoirs) ---- */
 enum { ROMIS_PASS_INITIAL = 0, ROMIS_PASS_TEMPORAL = 1, ROMIS_PASS_SPATIAL0 = 2 /* + pass */, ROMIS_PASS_FINAL = 1000 };

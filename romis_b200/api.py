@@ -24,7 +24,9 @@ EXPORTS = [
     "romis_frame_begin", "romis_frame_spatial_pass", "romis_frame_end", "romis_halo_region", "romis_stream",
     "romis_set_capture", "romis_download_reservoirs", "romis_download_gbuffer", "romis_trace_rays",
     "romis_set_stage_timing", "romis_last_frame_timings", "romis_host_alloc", "romis_host_free",
+    "romis_row_hit_counts", "romis_band_prepare", "romis_peer_export", "romis_peer_attach", "romis_peer_detach", "romis_peer_error",
 ]
+PEER_BLOB_BYTES = 512
 
 
 class RomisError(RuntimeError):
@@ -63,6 +65,12 @@ def load_library() -> C.CDLL:
     L.romis_download_gbuffer.argtypes = [vp, C.POINTER(abi.romis_gbuffer_dump)]
     L.romis_trace_rays.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]
     L.romis_last_frame_timings.argtypes = [vp, C.POINTER(abi.romis_timings)]
+    L.romis_row_hit_counts.argtypes = [vp, C.POINTER(abi.romis_camera), ci, ci, vp]
+    L.romis_band_prepare.argtypes = [vp, C.POINTER(abi.romis_features), ci, ci]
+    L.romis_peer_export.argtypes = [vp, vp]
+    L.romis_peer_attach.argtypes = [vp, vp, vp]
+    L.romis_peer_detach.argtypes = [vp]
+    L.romis_peer_error.argtypes = [vp, C.POINTER(ci)]
     L.romis_host_alloc.restype = vp; L.romis_host_alloc.argtypes = [C.c_size_t]
     L.romis_host_free.argtypes = [vp]; L.romis_host_free.restype = None
     _lib = L
@@ -211,6 +219,35 @@ class RestirRenderer:
         ptr = C.c_void_p(); n = C.c_size_t()
         self._check(self.lib.romis_halo_region(self.ctx, which, C.byref(ptr), C.byref(n)))
         return ptr.value or 0, n.value
+
+    def row_hit_counts(self, camera, W: int, H: int) -> np.ndarray:
+        cam = self._cam(camera, W, H)
+        out = np.zeros(H, np.uint32)
+        self._check(self.lib.romis_row_hit_counts(self.ctx, C.byref(cam), W, H, out.ctypes.data))
+        return out
+
+    # ---- peer-mapped halos (romis_peer_*) ----
+    def band_prepare(self, features: Features, W: int, H: int):
+        f = features.to_abi()
+        self._check(self.lib.romis_band_prepare(self.ctx, C.byref(f), W, H))
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(PEER_BLOB_BYTES)
+        self._check(self.lib.romis_peer_export(self.ctx, buf))
+        return bytes(buf.raw)
+
+    def peer_attach(self, low: bytes | None, high: bytes | None):
+        lo = C.create_string_buffer(low, PEER_BLOB_BYTES) if low else None
+        hi = C.create_string_buffer(high, PEER_BLOB_BYTES) if high else None
+        self._check(self.lib.romis_peer_attach(self.ctx, lo, hi))
+
+    def peer_detach(self):
+        self._check(self.lib.romis_peer_detach(self.ctx))
+
+    def peer_timed_out(self) -> bool:
+        e = C.c_int()
+        self._check(self.lib.romis_peer_error(self.ctx, C.byref(e)))
+        return bool(e.value)
 
     def stream(self) -> int:
         s = C.c_void_p()

@@ -22,6 +22,27 @@ def band_rows(height: int, world_size: int, rank: int) -> Tuple[int, int]:
     return (rank * height) // world_size, ((rank + 1) * height) // world_size
 
 
+def balanced_band_edges(row_cost, world_size: int, min_rows: int):
+    """Cuts rows into `world_size` contiguous bands of (nearly) equal total cost, each at least `min_rows` tall.
+    Deterministic, so every rank derives the same edges from the same cost profile.  Returns world_size + 1 edges."""
+    import numpy as np
+    cost = np.asarray(row_cost, np.float64)
+    H = len(cost)
+    min_rows = max(1, int(min_rows))
+    if world_size * min_rows > H:
+        raise ValueError(f"{world_size} bands of at least {min_rows} rows do not fit {H} rows")
+    prefix = np.concatenate([[0.0], np.cumsum(cost)])
+    edges = [0]
+    for g in range(1, world_size):
+        target = prefix[-1] * g / world_size
+        e = int(np.searchsorted(prefix, target))
+        e = max(e, edges[-1] + min_rows)                        # this band tall enough
+        e = min(e, H - (world_size - g) * min_rows)             # room for the remaining bands
+        edges.append(e)
+    edges.append(H)
+    return edges
+
+
 def check_bands(height: int, world_size: int, radius: int) -> None:
     smallest = min(band_rows(height, world_size, r)[1] - band_rows(height, world_size, r)[0] for r in range(world_size))
     if world_size > 1 and smallest < radius:
@@ -64,18 +85,54 @@ def exchange_halos(send_low: Optional[torch.Tensor], send_high: Optional[torch.T
 
 
 class BandedRenderer:
-    """Drives one `RestirRenderer` as rank `rank` of `world_size` row bands."""
+    """Drives one `RestirRenderer` as rank `rank` of `world_size` row bands.
 
-    def __init__(self, renderer, rank: int, world_size: int, device: torch.device):
+    transport "peer" (default): halo rows are pushed into the neighbours' buffers through CUDA-IPC mapped memory and
+    ordered by device-side flags inside romis_frame_spatial_pass (include/romis_gpu.h romis_peer_*): torch.distributed is
+    used once, to swap the 512-byte IPC blobs.  transport "nccl": batch_isend_irecv per pass (portable baseline)."""
+
+    def __init__(self, renderer, rank: int, world_size: int, device: torch.device, transport: str = "peer"):
         self.r = renderer
         self.rank, self.world_size, self.device = rank, world_size, device
         self.stream = torch.cuda.ExternalStream(renderer.stream(), device=device)
         self._height = None
+        self.transport = transport if world_size > 1 else "none"
+        self._attached = None
+        self.edges = None           # explicit band edges (balanced_band_edges); None = equal row counts
+
+    def _attach_peers(self, features, W, H):
+        """prepare -> export -> swap blobs -> attach; redone when the frame geometry changes."""
+        key = (W, H, features.numSamplesInReservoir, features.spatialResampleRadius)
+        if self._attached == key:
+            return
+        if self._attached is not None:
+            self.r.peer_detach()
+        self.r.band_prepare(features, W, H)
+        blobs = [None] * self.world_size
+        dist.all_gather_object(blobs, self.r.peer_export())
+        self.r.peer_attach(blobs[self.rank - 1] if self.rank > 0 else None,
+                           blobs[self.rank + 1] if self.rank < self.world_size - 1 else None)
+        dist.barrier()
+        self._attached = key
+
+    def balance(self, camera, W: int, H: int, radius: int, miss_cost: float = 0.04):
+        """Equal-COST bands for this camera: hit pixels carry the work of every pass, miss pixels short-circuit
+        (cost ratio measured on B200).  Every rank derives the same edges from romis_row_hit_counts; call it before the
+        first frame (moving the edges later drops the temporal history of the rows that change owner)."""
+        hits = self.r.row_hit_counts(camera, W, H).astype("float64")
+        self.edges = balanced_band_edges(hits + miss_cost * (W - hits), self.world_size, max(radius, 1))
+        self._height = None
+
+    def band(self, height: int):
+        if self.edges is not None and self.edges[-1] == height:
+            return self.edges[self.rank], self.edges[self.rank + 1]
+        return band_rows(height, self.world_size, self.rank)
 
     def set_height(self, height: int, radius: int):
         if self._height != height:
-            check_bands(height, self.world_size, radius)
-            y0, y1 = band_rows(height, self.world_size, self.rank)
+            if self.edges is None or self.edges[-1] != height:
+                check_bands(height, self.world_size, radius)
+            y0, y1 = self.band(height)
             self.r.set_band(y0, y1)
             self._height = height
 
@@ -83,11 +140,13 @@ class BandedRenderer:
         """The banded frame.  All work (kernels and transfers) is ordered on the renderer's own stream."""
         self.set_height(H, features.spatialResampleRadius if features.spatialReuse else 0)
         r = self.r
+        if self.transport == "peer" and features.spatialReuse:
+            self._attach_peers(features, W, H)
         with torch.cuda.stream(self.stream):
             r.frame_begin(features, camera, W, H, history_valid, seed, frame)
             if features.spatialReuse:
                 for p in range(features.spatialResamplingPasses):
-                    if self.world_size > 1:
+                    if self.transport == "nccl":
                         t = [alias_device_bytes(*r.halo_region(w), self.device) for w in
                              (abi.ROMIS_HALO_SEND_LOW, abi.ROMIS_HALO_SEND_HIGH, abi.ROMIS_HALO_RECV_LOW, abi.ROMIS_HALO_RECV_HIGH)]
                         exchange_halos(t[0], t[1], t[2], t[3], self.rank, self.world_size)

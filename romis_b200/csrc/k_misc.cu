@@ -80,6 +80,39 @@ __global__ void trace_kernel(SceneDev sc, const float* __restrict__ o, const flo
     if (h) { t[i] = tt; u[i] = uu; v[i] = vv; tri[i] = ti; }
 }
 
+// hit pixels per image row (romis_row_hit_counts): one warp per row
+__global__ void row_hits_kernel(GBufDev g, int W, int H, uint32_t n_meshes, uint32_t* rows) {
+    int y = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (y >= H) return;
+    uint32_t n = 0;
+    for (int x = lane; x < W; x += 32) n += g.mesh[(size_t)y * W + x] != n_meshes;
+    for (int o = 16; o; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if (lane == 0) rows[y] = n;
+}
+
+// Flag words of the peer-mapped halo protocol (romis_gpu.cu peer_exchange).  signal: publish a token into a neighbour's
+// flag word after everything earlier in the stream (the halo push) has completed.  wait: hold the stream until both
+// neighbours' tokens have arrived; the writer runs on ANOTHER GPU, so the spin cannot starve it.  A bounded spin
+// (~2 s) records a timeout instead of hanging the device if a neighbour never arrives.
+__global__ void signal_kernel(volatile uint32_t* a, uint32_t va, volatile uint32_t* b, uint32_t vb) {
+    __threadfence_system();
+    if (a) *a = va;
+    if (b) *b = vb;
+    __threadfence_system();
+}
+__global__ void wait_kernel(const volatile uint32_t* a, uint32_t va, const volatile uint32_t* b, uint32_t vb, uint32_t* err) {
+    const long long t0 = clock64();
+    bool okA = a == nullptr, okB = b == nullptr;
+    while (!(okA && okB)) {
+        if (!okA) okA = (int32_t)(*a - va) >= 0;
+        if (!okB) okB = (int32_t)(*b - vb) >= 0;
+        if (okA && okB) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }
+    }
+    __threadfence_system();
+}
+
 // unpack a reservoir buffer into the flat arrays of romis_reservoir_dump (parity read-back)
 __global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, uint32_t* light, float* u, float* v, float* W, uint32_t* M,
                             float* pos, float* col) {
@@ -112,6 +145,15 @@ void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& 
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {
     trace_kernel<<<(n + 127) / 128, 128, 0, s>>>(sc, o, d, tfar, n, any_hit, hit, t, u, v, tri);
+}
+void launch_row_hits(cudaStream_t s, const GBufDev& g, int W, int H, int n_meshes, uint32_t* rows) {
+    row_hits_kernel<<<(H + 7) / 8, 256, 0, s>>>(g, W, H, (uint32_t)n_meshes, rows);
+}
+void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb) {
+    if (a || b) signal_kernel<<<1, 1, 0, s>>>(a, va, b, vb);
+}
+void launch_wait(cudaStream_t s, const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb, uint32_t* err) {
+    if (a || b) wait_kernel<<<1, 1, 0, s>>>(a, va, b, vb, err);
 }
 void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
                  uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col) {

@@ -12,6 +12,9 @@ void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased,
 void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb);
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
+void launch_row_hits(cudaStream_t s, const GBufDev& g, int W, int H, int n_meshes, uint32_t* rows);
+void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb);
+void launch_wait(cudaStream_t s, const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb, uint32_t* err);
 void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
                  uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col);
 }  // namespace romis

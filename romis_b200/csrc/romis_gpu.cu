@@ -64,6 +64,18 @@ struct romis_ctx {
     int next_pass = 0;
     int n_launches = 0;
 
+    // peer-mapped halos (one process per GPU; see romis_peer_attach)
+    struct Peer {
+        bool on = false;
+        unsigned char* res[3] = {nullptr, nullptr, nullptr};   // the neighbour's three reservoir buffers, IPC-mapped
+        uint32_t* flags = nullptr;                              // the neighbour's flag words, IPC-mapped
+        int y0 = 0, y1 = 0, ey0 = 0, ey1 = 0;
+        size_t row_stride = 0;
+    } peer[2];                          // [0] = band below (smaller y), [1] = band above
+    DevBuf flags;                       // my flag words: {ready_from_low, ready_from_high, done_from_low, done_from_high, error}
+    uint32_t pass_token = 0, frame_token = 0;
+    bool exported = false;
+
     // parity capture
     bool capture = false;
     std::map<int, DevBuf> captured;
@@ -137,12 +149,15 @@ extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** ou
     return ROMIS_OK;
 }
 
+extern "C" int romis_peer_detach(romis_ctx* c);
 extern "C" void romis_destroy(romis_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
                       &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2]}) b->release();
+    romis_peer_detach(c);
+    c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
     for (cudaEvent_t e : c->ev_stage) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -321,19 +336,16 @@ static int capture_stage(romis_ctx* c, int pass_id, int buf) {
 static const dim3 kBlock(32, 8);
 static dim3 grid_for(int W, int rows) { return dim3((W + kBlock.x - 1) / kBlock.x, (rows + kBlock.y - 1) / kBlock.y); }
 
-extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
-                                 int history_valid, const romis_rng* rng) {
-    if (!c) return ROMIS_ERR_INVALID;
-    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_begin: previous frame not ended");
-    int rc = validate(c, f, cam, W, H, rng);
-    if (rc) return rc;
-    RCHECK(c, cudaSetDevice(c->device));
+// (Re)allocates the per-frame buffers for (W, H, N, band, halo).  A change of resolution, band or N drops the temporal
+// history (the reference would read out of bounds).
+static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, int H) {
     const int N = (int)f->numSamplesInReservoir;
     int y0 = 0, y1 = H;
     if (c->band_y1 > c->band_y0) { y0 = c->band_y0; y1 = c->band_y1; if (y1 > H) return fail(c, ROMIS_ERR_INVALID, "band exceeds the image height"); }
     const int halo = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
     if (W != c->W || H != c->H || N != c->N || halo > c->halo || y0 != c->y0 || y1 != c->y1) {
-        // (re)allocate; a change of resolution or N drops the temporal history
+        if (c->peer[0].on || c->peer[1].on || c->exported)
+            return fail(c, ROMIS_ERR_STATE, "frame geometry changed after romis_peer_export: detach, prepare, export and attach again");
         RCHECK(c, cudaStreamSynchronize(c->stream));
         c->W = W; c->H = H; c->N = N; c->halo = halo; c->y0 = y0; c->y1 = y1;
         c->ey0 = std::max(0, y0 - halo); c->ey1 = std::min(H, y1 + halo);
@@ -352,6 +364,17 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
         for (auto& kv : c->captured) kv.second.release();
         c->captured.clear();
     }
+    return ROMIS_OK;
+}
+
+extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
+                                 int history_valid, const romis_rng* rng) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_begin: previous frame not ended");
+    int rc = validate(c, f, cam, W, H, rng);
+    if (rc) return rc;
+    RCHECK(c, cudaSetDevice(c->device));
+    if ((rc = ensure_frame_buffers(c, f, W, H))) return rc;
     if (!history_valid) c->history_valid = false;
 
     FrameDev& fr = c->fr;
@@ -401,6 +424,164 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     return ROMIS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// peer-mapped halos: the boundary rows of the buffer the next spatial pass reads are pushed straight into the
+// neighbouring bands' halo rows over NVLink (IPC-mapped device memory), ordered by flag words: no NCCL, no host sync.
+//   ready flags  token = running count of spatial passes: "my rows for this pass are in your halo"
+//   done flags   token = running count of frames:         "I finished the frame's last pass, your rows in my halo are free"
+// RAW: a pass waits for both neighbours' ready token.  WAR: the buffer a pass p >= 1 pushes into was last read by the
+// neighbour's pass p-2, which completed before it sent ready(p-1) -- already waited for; for pass 0 the last reader may be
+// the previous frame's final pass, hence the done flags.
+// ------------------------------------------------------------------------------------------------
+struct PeerBlob {
+    uint32_t magic;
+    int32_t W, H, N, y0, y1, ey0, ey1;
+    uint64_t row_stride;
+    cudaIpcMemHandle_t res[3];
+    cudaIpcMemHandle_t flags;
+};
+static_assert(sizeof(PeerBlob) <= ROMIS_PEER_BLOB_BYTES, "peer blob fits the ABI buffer");
+
+static int peer_exchange(romis_ctx* c, int in, int pass) {
+    const int r = (int)c->fr.f.spatialResampleRadius;
+    uint32_t* my = (uint32_t*)c->flags.p;
+    if (pass == 0) {
+        // WAR guard for the first push of a frame (see above); frame_token counts completed frames
+        launch_wait(c->stream, c->peer[0].on ? my + 2 : nullptr, c->frame_token, c->peer[1].on ? my + 3 : nullptr, c->frame_token, my + 4);
+    }
+    c->pass_token++;
+    const unsigned char* src = (const unsigned char*)c->res[in].p;
+    if (c->peer[0].on) {    // my lowest r rows -> the upper halo of the band below
+        const romis_ctx::Peer& p = c->peer[0];
+        RCHECK(c, cudaMemcpyAsync(p.res[in] + (size_t)(c->y0 - p.ey0) * p.row_stride, src + (size_t)(c->y0 - c->ey0) * c->row_stride,
+                                  (size_t)r * c->row_stride, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (c->peer[1].on) {    // my highest r rows -> the lower halo of the band above
+        const romis_ctx::Peer& p = c->peer[1];
+        RCHECK(c, cudaMemcpyAsync(p.res[in] + (size_t)(c->y1 - r - p.ey0) * p.row_stride, src + (size_t)(c->y1 - r - c->ey0) * c->row_stride,
+                                  (size_t)r * c->row_stride, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    launch_signal(c->stream, c->peer[0].on ? c->peer[0].flags + 1 : nullptr, c->pass_token, c->peer[1].on ? c->peer[1].flags + 0 : nullptr, c->pass_token);
+    launch_wait(c->stream, c->peer[0].on ? my + 0 : nullptr, c->pass_token, c->peer[1].on ? my + 1 : nullptr, c->pass_token, my + 4);
+    RCHECK(c, cudaGetLastError());
+    return ROMIS_OK;
+}
+
+// Per-row count of pixels whose primary ray hits geometry, for the whole frame: the work of every pass is concentrated in
+// hit pixels (miss pixels short-circuit), so hosts use this profile to cut the frame into equal-cost row bands.  Every rank
+// computes the same profile from the same scene and camera, so the band edges agree without communication.
+extern "C" int romis_row_hit_counts(romis_ctx* c, const romis_camera* cam, int W, int H, uint32_t* hits_per_row) {
+    if (!c || !cam || !hits_per_row || W < 1 || H < 1) return ROMIS_ERR_INVALID;
+    if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_row_hit_counts: frame in flight");
+    RCHECK(c, cudaSetDevice(c->device));
+    DevBuf tn, mesh, uv, rows;
+    auto done = [&](int code) { tn.release(); mesh.release(); uv.release(); rows.release(); return code; };
+    const size_t px = (size_t)W * H;
+    cudaError_t e = tn.ensure(px * sizeof(float4));
+    if (e == cudaSuccess) e = mesh.ensure(px * sizeof(uint32_t));
+    if (e == cudaSuccess) e = uv.ensure(c->sc.has_textures ? px * sizeof(float2) : 16);
+    if (e == cudaSuccess) e = rows.ensure((size_t)H * sizeof(uint32_t));
+    if (e != cudaSuccess) return done(fail(c, ROMIS_ERR_NOMEM, std::string("romis_row_hit_counts: ") + cudaGetErrorString(e)));
+    FrameDev fr; std::memset(&fr, 0, sizeof fr);
+    fr.cam.origin.x = cam->origin[0]; fr.cam.origin.y = cam->origin[1]; fr.cam.origin.z = cam->origin[2];
+    fr.cam.qw = cam->quat[0]; fr.cam.qx = cam->quat[1]; fr.cam.qy = cam->quat[2]; fr.cam.qz = cam->quat[3];
+    fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
+    fr.W = W; fr.H = H; fr.y0 = 0; fr.y1 = H; fr.ey0 = 0; fr.ey1 = H;
+    GBufDev g; g.tn = (float4*)tn.p; g.mesh = (uint32_t*)mesh.p; g.uv = (float2*)uv.p;
+    launch_primary(c->stream, grid_for(W, H), kBlock, c->sc, fr, g, 0, H);
+    launch_row_hits(c->stream, g, W, H, c->sc.n_meshes, (uint32_t*)rows.p);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits_per_row, rows.p, (size_t)H * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(c, ROMIS_ERR_CUDA, std::string("romis_row_hit_counts: ") + cudaGetErrorString(e)));
+    return done(ROMIS_OK);
+}
+
+extern "C" int romis_band_prepare(romis_ctx* c, const romis_features* f, int W, int H) {
+    if (!c || !f) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_band_prepare: frame in flight");
+    if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
+    if (f->numSamplesInReservoir < 1 || f->numSamplesInReservoir > 32 || W < 1 || H < 1) return fail(c, ROMIS_ERR_INVALID, "romis_band_prepare: bad parameters");
+    RCHECK(c, cudaSetDevice(c->device));
+    int rc = ensure_frame_buffers(c, f, W, H);
+    if (rc) return rc;
+    RCHECK(c, c->flags.ensure(8 * sizeof(uint32_t)));
+    RCHECK(c, cudaMemsetAsync(c->flags.p, 0, 8 * sizeof(uint32_t), c->stream));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    c->pass_token = 0; c->frame_token = 0;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_peer_export(romis_ctx* c, void* blob) {
+    if (!c || !blob) return ROMIS_ERR_INVALID;
+    if (!c->W || !c->flags.p) return fail(c, ROMIS_ERR_STATE, "romis_peer_export: call romis_band_prepare first");
+    RCHECK(c, cudaSetDevice(c->device));
+    PeerBlob b; std::memset(&b, 0, sizeof b);
+    b.magic = 0x524d5042u; b.W = c->W; b.H = c->H; b.N = c->N; b.y0 = c->y0; b.y1 = c->y1; b.ey0 = c->ey0; b.ey1 = c->ey1;
+    b.row_stride = c->row_stride;
+    for (int i = 0; i < 3; i++) RCHECK(c, cudaIpcGetMemHandle(&b.res[i], c->res[i].p));
+    RCHECK(c, cudaIpcGetMemHandle(&b.flags, c->flags.p));
+    std::memset(blob, 0, ROMIS_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof b);
+    c->exported = true;
+    return ROMIS_OK;
+}
+
+static int attach_one(romis_ctx* c, int side, const void* blob) {
+    PeerBlob b; std::memcpy(&b, blob, sizeof b);
+    if (b.magic != 0x524d5042u) return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: not a peer blob");
+    if (b.W != c->W || b.H != c->H || b.N != c->N || b.row_stride != c->row_stride) return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: neighbour renders a different frame geometry");
+    if ((side == 0 && b.y1 != c->y0) || (side == 1 && b.y0 != c->y1)) return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: bands are not adjacent");
+    romis_ctx::Peer& p = c->peer[side];
+    for (int i = 0; i < 3; i++) RCHECK(c, cudaIpcOpenMemHandle((void**)&p.res[i], b.res[i], cudaIpcMemLazyEnablePeerAccess));
+    RCHECK(c, cudaIpcOpenMemHandle((void**)&p.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
+    p.y0 = b.y0; p.y1 = b.y1; p.ey0 = b.ey0; p.ey1 = b.ey1; p.row_stride = (size_t)b.row_stride;
+    p.on = true;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_peer_detach(romis_ctx* c) {
+    if (!c) return ROMIS_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < 2; s++) {
+        romis_ctx::Peer& p = c->peer[s];
+        if (!p.on) continue;
+        for (int i = 0; i < 3; i++) if (p.res[i]) cudaIpcCloseMemHandle(p.res[i]);
+        if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        p = romis_ctx::Peer();
+    }
+    c->exported = false;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_peer_attach(romis_ctx* c, const void* low_blob, const void* high_blob) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_peer_attach: frame in flight");
+    if (!c->W || !c->flags.p) return fail(c, ROMIS_ERR_STATE, "romis_peer_attach: call romis_band_prepare first");
+    if ((low_blob != nullptr) != (c->y0 > 0) || (high_blob != nullptr) != (c->y1 < c->H))
+        return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: need exactly the neighbours this band has");
+    if (c->y1 - c->y0 < c->halo) return fail(c, ROMIS_ERR_INVALID, "band has fewer rows than the spatial radius");
+    RCHECK(c, cudaSetDevice(c->device));
+    int rc = ROMIS_OK;
+    if (low_blob) rc = attach_one(c, 0, low_blob);
+    if (rc == ROMIS_OK && high_blob) rc = attach_one(c, 1, high_blob);
+    if (rc != ROMIS_OK) { std::string keep = c->err; romis_peer_detach(c); c->err = keep; }
+    return rc;
+}
+
+extern "C" int romis_peer_error(romis_ctx* c, int* timed_out) {
+    if (!c || !timed_out) return ROMIS_ERR_INVALID;
+    *timed_out = 0;
+    if (!c->flags.p) return ROMIS_OK;
+    RCHECK(c, cudaSetDevice(c->device));
+    uint32_t e = 0;
+    RCHECK(c, cudaMemcpy(&e, (uint32_t*)c->flags.p + 4, 4, cudaMemcpyDeviceToHost));
+    *timed_out = (int)e;
+    return ROMIS_OK;
+}
+
 extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     if (!c) return ROMIS_ERR_INVALID;
     if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_spatial_pass: no frame in flight");
@@ -410,6 +591,7 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     // ping-pong between the two work buffers; the history buffer is never written during a frame
     const int in = c->cur, out = c->spare;
     const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
+    if (c->peer[0].on || c->peer[1].on) { int prc = peer_exchange(c, in, pass); if (prc) return prc; }
     launch_spatial(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass);
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
@@ -419,6 +601,13 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     c->spare = in;
     c->cur = out;
     c->next_pass++;
+    if ((c->peer[0].on || c->peer[1].on) && pass + 1 == (int)c->fr.f.spatialResamplingPasses) {
+        // last pass of the frame: tell the neighbours that their rows in my halo regions are no longer being read
+        c->frame_token++;
+        launch_signal(c->stream, c->peer[0].on ? c->peer[0].flags + 3 : nullptr, c->frame_token,
+                      c->peer[1].on ? c->peer[1].flags + 2 : nullptr, c->frame_token);
+        RCHECK(c, cudaGetLastError());
+    }
     return ROMIS_OK;
 }
 

@@ -212,7 +212,10 @@ def main():
     r.upload_scene(scene)
     br = BandedRenderer(r, rank, world, device, transport=args.halo)
     if world > 1 and not args.equal_rows:
+        # equal-COST bands: first cut from the primary-ray hit profile, then refined from measured per-band compute times
+        # (untimed, before the warm-up; the camera of this workload is static)
         br.balance(cam, W, H, feat.spatialResampleRadius if feat.spatialReuse else 0)
+        br.calibrate(feat, cam, W, H, seed=SEED)
     N = feat.numSamplesInReservoir
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 

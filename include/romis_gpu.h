@@ -227,6 +227,7 @@ typedef struct romis_timings {          /* device time of the last frame, millis
     float total_ms;                     /* first kernel start .. last kernel end (no read-back) */
     int32_t n_spatial;
     int32_t n_launches;                 /* kernels launched for the frame */
+    float exchange_ms[8];               /* peer-mapped halo push + wait before each spatial pass (not part of spatial_ms) */
 } romis_timings;
 /* Per-stage events are recorded only when enabled (they break the frame's CUDA graph into
  * stream launches); total_ms is always available. */

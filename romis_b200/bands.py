@@ -123,6 +123,44 @@ class BandedRenderer:
         self.edges = balanced_band_edges(hits + miss_cost * (W - hits), self.world_size, max(radius, 1))
         self._height = None
 
+    def calibrate(self, features, camera, W: int, H: int, seed: int = 1, rounds: int = 3, frames: int = 3):
+        """Measured refinement of the band edges (static camera): render a few frames, take every rank's own compute time
+        (all pass kernels; the wait for the neighbours' halo rows is timed separately), turn it into a per-row cost density
+        and recut.  Cost per hit pixel varies across the
+        image (e.g. surfaces facing away from most lights take the `NL < 0` early exit), which the hit-count profile
+        cannot see.  Moving an edge re-allocates the band, so history is dropped and peers are re-attached: call this
+        before the frames that matter."""
+        import numpy as np
+        if self.world_size == 1:
+            return
+        radius = features.spatialResampleRadius if features.spatialReuse else 0
+        if self.edges is None:
+            self.edges = [band_rows(H, self.world_size, g)[0] for g in range(self.world_size)] + [H]
+        for _ in range(rounds):
+            self.r.set_stage_timing(True)
+            t_local = 0.0
+            for fr in range(frames + 1):
+                self.render_frame(features, camera, W, H, fr > 0, seed, fr, out=None)
+                self.r.synchronize()
+                t = self.r.timings()
+                if fr > 0:       # own compute only: the wait for the neighbours is reported separately (exchange_ms)
+                    t_local += t.primary_ms + t.initial_ms + t.temporal_ms + t.shade_ms + sum(t.spatial_ms[:t.n_spatial])
+            self.r.set_stage_timing(False)
+            times = [None] * self.world_size
+            dist.all_gather_object(times, t_local / frames)
+            cost = np.zeros(H)
+            for g in range(self.world_size):
+                a, b = self.edges[g], self.edges[g + 1]
+                cost[a:b] = times[g] / max(1, b - a)
+            new_edges = balanced_band_edges(cost, self.world_size, max(radius, 1))
+            if new_edges == self.edges:
+                break
+            if self._attached is not None:
+                self.r.peer_detach(); self._attached = None
+            self.edges = new_edges
+            self._height = None
+        self.r.reset_history()
+
     def band(self, height: int):
         if self.edges is not None and self.edges[-1] == height:
             return self.edges[self.rank], self.edges[self.rank + 1]

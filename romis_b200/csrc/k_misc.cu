@@ -113,6 +113,49 @@ __global__ void wait_kernel(const volatile uint32_t* a, uint32_t va, const volat
     __threadfence_system();
 }
 
+// The whole halo exchange of one spatial pass as ONE kernel (peer_exchange in romis_gpu.cu):
+//   1. (first pass of a frame) wait until the neighbours have finished reading their halo rows of this buffer,
+//   2. copy my boundary rows into the neighbours' halo rows -- plain 128-bit stores to IPC-mapped peer memory over NVLink,
+//   3. the last block to finish publishes the pass token to both neighbours and then holds the kernel (and with it the
+//      stream, i.e. the spatial pass behind it) until the neighbours' tokens have arrived.
+// The neighbours run on OTHER GPUs, so waiting cannot starve the writer; spins are bounded (~2 s) and report a timeout.
+__device__ __forceinline__ bool spin_until(const volatile uint32_t* f, uint32_t token, uint32_t* err) {
+    if (!f) return true;
+    const long long t0 = clock64();
+    while ((int32_t)(*f - token) < 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000LL) { *err = 1u; return false; }
+    }
+    return true;
+}
+__global__ void __launch_bounds__(256) halo_push_kernel(const uint4* __restrict__ src_low, uint4* __restrict__ dst_low, size_t n_low,
+                                                        const uint4* __restrict__ src_high, uint4* __restrict__ dst_high, size_t n_high,
+                                                        const volatile uint32_t* war_a, const volatile uint32_t* war_b, uint32_t war_token,
+                                                        volatile uint32_t* sig_a, volatile uint32_t* sig_b, uint32_t token,
+                                                        const volatile uint32_t* wait_a, const volatile uint32_t* wait_b,
+                                                        uint32_t* err, unsigned int* ticket) {
+    if (threadIdx.x == 0) { spin_until(war_a, war_token, err); spin_until(war_b, war_token, err); }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < n_low; i += stride) dst_low[i] = src_low[i];
+    for (size_t i = t; i < n_high; i += stride) dst_high[i] = src_high[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int mine = atomicAdd(ticket, 1u);
+        if (mine == gridDim.x - 1) {
+            __threadfence_system();
+            *ticket = 0u;
+            if (sig_a) *sig_a = token;
+            if (sig_b) *sig_b = token;
+            __threadfence_system();
+            spin_until(wait_a, token, err);
+            spin_until(wait_b, token, err);
+            __threadfence_system();
+        }
+    }
+}
+
 // unpack a reservoir buffer into the flat arrays of romis_reservoir_dump (parity read-back)
 __global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, uint32_t* light, float* u, float* v, float* W, uint32_t* M,
                             float* pos, float* col) {
@@ -148,6 +191,12 @@ void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, con
 }
 void launch_row_hits(cudaStream_t s, const GBufDev& g, int W, int H, int n_meshes, uint32_t* rows) {
     row_hits_kernel<<<(H + 7) / 8, 256, 0, s>>>(g, W, H, (uint32_t)n_meshes, rows);
+}
+void launch_halo_push(cudaStream_t s, const void* src_low, void* dst_low, size_t bytes_low, const void* src_high, void* dst_high, size_t bytes_high,
+                      const uint32_t* war_a, const uint32_t* war_b, uint32_t war_token, uint32_t* sig_a, uint32_t* sig_b, uint32_t token,
+                      const uint32_t* wait_a, const uint32_t* wait_b, uint32_t* err, unsigned int* ticket) {
+    halo_push_kernel<<<32, 256, 0, s>>>((const uint4*)src_low, (uint4*)dst_low, bytes_low / 16, (const uint4*)src_high, (uint4*)dst_high, bytes_high / 16,
+                                        war_a, war_b, war_token, sig_a, sig_b, token, wait_a, wait_b, err, ticket);
 }
 void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb) {
     if (a || b) signal_kernel<<<1, 1, 0, s>>>(a, va, b, vb);

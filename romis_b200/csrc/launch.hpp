@@ -13,6 +13,9 @@ void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& 
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
 void launch_row_hits(cudaStream_t s, const GBufDev& g, int W, int H, int n_meshes, uint32_t* rows);
+void launch_halo_push(cudaStream_t s, const void* src_low, void* dst_low, size_t bytes_low, const void* src_high, void* dst_high, size_t bytes_high,
+                      const uint32_t* war_a, const uint32_t* war_b, uint32_t war_token, uint32_t* sig_a, uint32_t* sig_b, uint32_t token,
+                      const uint32_t* wait_a, const uint32_t* wait_b, uint32_t* err, unsigned int* ticket);
 void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb);
 void launch_wait(cudaStream_t s, const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb, uint32_t* err);
 void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,

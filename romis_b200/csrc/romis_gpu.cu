@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -333,7 +334,14 @@ static int capture_stage(romis_ctx* c, int pass_id, int buf) {
     return ROMIS_OK;
 }
 
-static const dim3 kBlock(32, 8);
+// Block shape of the pass kernels (launch bounds are for 256 threads; smaller blocks only shorten the tail of short
+// kernels, e.g. thin row bands).  ROMIS_BLOCK_Y=<n> in the environment overrides it for tuning runs.
+static dim3 make_block() {
+    int by = 8;
+    if (const char* e = std::getenv("ROMIS_BLOCK_Y")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) by = v; }
+    return dim3(32, by);
+}
+static const dim3 kBlock = make_block();
 static dim3 grid_for(int W, int rows) { return dim3((W + kBlock.x - 1) / kBlock.x, (rows + kBlock.y - 1) / kBlock.y); }
 
 // (Re)allocates the per-frame buffers for (W, H, N, band, halo).  A change of resolution, band or N drops the temporal
@@ -444,32 +452,25 @@ static_assert(sizeof(PeerBlob) <= ROMIS_PEER_BLOB_BYTES, "peer blob fits the ABI
 
 static int peer_exchange(romis_ctx* c, int in, int pass) {
     const int r = (int)c->fr.f.spatialResampleRadius;
-    uint32_t* my = (uint32_t*)c->flags.p;
-    if (pass == 0) {
-        // WAR guard for the first push of a frame (see above); frame_token counts completed frames
-        launch_wait(c->stream, c->peer[0].on ? my + 2 : nullptr, c->frame_token, c->peer[1].on ? my + 3 : nullptr, c->frame_token, my + 4);
-    }
+    uint32_t* my = (uint32_t*)c->flags.p;      // {ready_from_low, ready_from_high, done_from_low, done_from_high, error, ticket}
     c->pass_token++;
     const unsigned char* src = (const unsigned char*)c->res[in].p;
-    if (c->peer[0].on) {    // my lowest r rows -> the upper halo of the band below
-        const romis_ctx::Peer& p = c->peer[0];
-        RCHECK(c, cudaMemcpyAsync(p.res[in] + (size_t)(c->y0 - p.ey0) * p.row_stride, src + (size_t)(c->y0 - c->ey0) * c->row_stride,
-                                  (size_t)r * c->row_stride, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    if (c->peer[1].on) {    // my highest r rows -> the lower halo of the band above
-        const romis_ctx::Peer& p = c->peer[1];
-        RCHECK(c, cudaMemcpyAsync(p.res[in] + (size_t)(c->y1 - r - p.ey0) * p.row_stride, src + (size_t)(c->y1 - r - c->ey0) * c->row_stride,
-                                  (size_t)r * c->row_stride, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    launch_signal(c->stream, c->peer[0].on ? c->peer[0].flags + 1 : nullptr, c->pass_token, c->peer[1].on ? c->peer[1].flags + 0 : nullptr, c->pass_token);
-    launch_wait(c->stream, c->peer[0].on ? my + 0 : nullptr, c->pass_token, c->peer[1].on ? my + 1 : nullptr, c->pass_token, my + 4);
+    const romis_ctx::Peer& lo = c->peer[0]; const romis_ctx::Peer& hi = c->peer[1];
+    const size_t bytes = (size_t)r * c->row_stride;     // row_stride is a multiple of 16
+    // my lowest r rows -> the upper halo of the band below; my highest r rows -> the lower halo of the band above
+    launch_halo_push(c->stream,
+                     lo.on ? src + (size_t)(c->y0 - c->ey0) * c->row_stride : nullptr, lo.on ? lo.res[in] + (size_t)(c->y0 - lo.ey0) * lo.row_stride : nullptr, lo.on ? bytes : 0,
+                     hi.on ? src + (size_t)(c->y1 - r - c->ey0) * c->row_stride : nullptr, hi.on ? hi.res[in] + (size_t)(c->y1 - r - hi.ey0) * hi.row_stride : nullptr, hi.on ? bytes : 0,
+                     (pass == 0 && lo.on) ? my + 2 : nullptr, (pass == 0 && hi.on) ? my + 3 : nullptr, c->frame_token,
+                     lo.on ? lo.flags + 1 : nullptr, hi.on ? hi.flags + 0 : nullptr, c->pass_token,
+                     lo.on ? my + 0 : nullptr, hi.on ? my + 1 : nullptr, my + 4, (unsigned int*)(my + 5));
     RCHECK(c, cudaGetLastError());
     return ROMIS_OK;
 }
 
-// Per-row count of pixels whose primary ray hits geometry, for the whole frame: the work of every pass is concentrated in
-// hit pixels (miss pixels short-circuit), so hosts use this profile to cut the frame into equal-cost row bands.  Every rank
-// computes the same profile from the same scene and camera, so the band edges agree without communication.
+// Per-row count of pixels whose primary ray hits geometry, for the whole frame: most of the work of every pass sits in
+// hit pixels (miss pixels short-circuit), so hosts use this profile as a first cut of the frame into equal-cost row bands.
+// Every rank computes the same profile from the same scene and camera, so the band edges agree without communication.
 extern "C" int romis_row_hit_counts(romis_ctx* c, const romis_camera* cam, int W, int H, uint32_t* hits_per_row) {
     if (!c || !cam || !hits_per_row || W < 1 || H < 1) return ROMIS_ERR_INVALID;
     if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
@@ -591,7 +592,7 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     // ping-pong between the two work buffers; the history buffer is never written during a frame
     const int in = c->cur, out = c->spare;
     const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
-    if (c->peer[0].on || c->peer[1].on) { int prc = peer_exchange(c, in, pass); if (prc) return prc; }
+    if (c->peer[0].on || c->peer[1].on) { int prc = peer_exchange(c, in, pass); if (prc) return prc; c->n_launches++; RCHECK(c, mark(c, 6, pass)); }
     launch_spatial(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass);
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
@@ -702,6 +703,7 @@ extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
                 case 3: t.temporal_ms = ms; break;
                 case 4: if (c->marks[i].idx < 8) t.spatial_ms[c->marks[i].idx] = ms; t.n_spatial = std::max(t.n_spatial, c->marks[i].idx + 1); break;
                 case 5: t.shade_ms = ms; break;
+                case 6: if (c->marks[i].idx < 8) t.exchange_ms[c->marks[i].idx] = ms; break;
             }
         }
         t.n_launches = c->n_launches;

@@ -13,7 +13,8 @@ scene = Scene.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golde
 feat = Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True); cam = Camera(); W, H = 1920, 1080
 r = RestirRenderer(local); r.upload_scene(scene); r.set_stage_timing(True)
 br = BandedRenderer(r, rank, world, device, transport=os.environ.get("HALO", "peer"))
-if world > 1 and os.environ.get("BALANCE", "1") == "1": br.balance(cam, W, H, 10)
+if world > 1 and os.environ.get("BALANCE", "1") == "1":
+    br.balance(cam, W, H, 10); br.calibrate(feat, cam, W, H); r.set_stage_timing(True)
 if world == 1 and len(sys.argv) > 2: r.set_band(int(sys.argv[1]), int(sys.argv[2])); br._height = H
 acc = None
 for fr in range(12):
@@ -21,8 +22,8 @@ for fr in range(12):
     torch.cuda.synchronize()
     br.render_frame(feat, cam, W, H, fr > 0, 1, fr, out=None); r.synchronize()
     t = r.timings()
-    row = np.array([t.total_ms, t.primary_ms, t.initial_ms, t.temporal_ms, *t.spatial_ms[:3], t.shade_ms])
+    row = np.array([t.total_ms, t.primary_ms, t.initial_ms, t.temporal_ms, *t.spatial_ms[:3], t.shade_ms, *t.exchange_ms[:3]])
     if fr >= 4: acc = row if acc is None else acc + row
 acc /= 8
-print(f"rank {rank} band {br.band(H) if world > 1 else sys.argv[1:3]}: total {acc[0]:.3f} primary {acc[1]:.3f} initial {acc[2]:.3f} temporal {acc[3]:.3f} spatial {acc[4]:.3f} {acc[5]:.3f} {acc[6]:.3f} shade {acc[7]:.3f}", flush=True)
+print(f"rank {rank} band {br.band(H) if world > 1 else sys.argv[1:3]}: total {acc[0]:.3f} primary {acc[1]:.3f} initial {acc[2]:.3f} temporal {acc[3]:.3f} spatial {acc[4]:.3f} {acc[5]:.3f} {acc[6]:.3f} shade {acc[7]:.3f} exchange {acc[8]:.3f} {acc[9]:.3f} {acc[10]:.3f}", flush=True)
 if world > 1: dist.destroy_process_group()

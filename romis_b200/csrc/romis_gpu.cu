@@ -84,6 +84,10 @@ struct romis_ctx {
     // timing
     bool stage_timing = false;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    void* light_stage = nullptr; size_t light_stage_bytes = 0;     // pinned staging of the packed light table
+    cudaEvent_t ev_lights = nullptr; bool light_copy_pending = false;
+    cudaStream_t copy_stream = nullptr;     // image read-back, overlapped with shading (romis_frame_end)
+    cudaEvent_t ev_chunk[8] = {};
     std::vector<cudaEvent_t> ev_stage;  // begin, after primary, after initial, after temporal, after spatial p..., after shade
     struct Mark { int kind; int idx; };
     std::vector<Mark> marks;
@@ -145,6 +149,9 @@ extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** ou
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_lights, cudaEventDisableTiming);
+    for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->ev_chunk[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { set_err(std::string("context setup: ") + cudaGetErrorString(e)); delete c; return ROMIS_ERR_CUDA; }
     *out = c;
     return ROMIS_OK;
@@ -163,6 +170,10 @@ extern "C" void romis_destroy(romis_ctx* c) {
     for (cudaEvent_t e : c->ev_stage) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    for (int k = 0; k < 8; k++) if (c->ev_chunk[k]) cudaEventDestroy(c->ev_chunk[k]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_lights) cudaEventDestroy(c->ev_lights);
+    if (c->light_stage) cudaFreeHost(c->light_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -278,15 +289,28 @@ static void pack_light(const romis_light& l, float4* r) {
 extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) {
     if (!c) return ROMIS_ERR_INVALID;
     if (n < 0 || (n > 0 && !lights)) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: bad arguments");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_upload_lights: frame in flight");
     RCHECK(c, cudaSetDevice(c->device));
-    std::vector<float4> rec(6 * (size_t)std::max(1, n));
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n; i++)
         if (lights[i].type > ROMIS_LIGHT_PARALLELOGRAM) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: unknown light type");
-        pack_light(lights[i], &rec[6 * (size_t)i]);
+    // Called every frame by the drop-in (the reference re-reads scene.lights every frame): pack into a pinned staging
+    // buffer and copy on the context's stream, ordered before the next frame's kernels, without a host synchronisation.
+    const size_t bytes = 6 * sizeof(float4) * (size_t)std::max(1, n);
+    if (c->light_stage_bytes < bytes) {
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+        if (c->light_stage) cudaFreeHost(c->light_stage);
+        c->light_stage = nullptr; c->light_stage_bytes = 0;
+        RCHECK(c, cudaMallocHost(&c->light_stage, bytes));
+        c->light_stage_bytes = bytes;
+        RCHECK(c, c->lights.ensure(bytes));
+    } else if (c->light_copy_pending) {
+        RCHECK(c, cudaEventSynchronize(c->ev_lights));      // the previous copy out of the staging buffer (long done)
     }
-    RCHECK(c, cudaStreamSynchronize(c->stream));
-    RCHECK(c, c->lights.ensure(rec.size() * sizeof(float4)));
-    RCHECK(c, cudaMemcpy(c->lights.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    float4* rec = (float4*)c->light_stage;
+    for (int i = 0; i < n; i++) pack_light(lights[i], rec + 6 * (size_t)i);
+    RCHECK(c, cudaMemcpyAsync(c->lights.p, rec, 6 * sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    RCHECK(c, cudaEventRecord(c->ev_lights, c->stream));
+    c->light_copy_pending = true;
     c->sc.lights = (const float4*)c->lights.p;
     c->sc.n_lights = n;
     return ROMIS_OK;
@@ -618,10 +642,25 @@ extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
     if (c->fr.f.spatialReuse && c->next_pass != (int)c->fr.f.spatialResamplingPasses)
         return fail(c, ROMIS_ERR_STATE, "romis_frame_end: spatial passes missing");
     RCHECK(c, cudaSetDevice(c->device));
-    const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
-    launch_shade(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, c->cur), (float*)c->rgb.p);
-    c->n_launches++;
-    RCHECK(c, cudaGetLastError());
+    // Shade + read-back.  With a host destination the band is shaded in a few row chunks and every chunk's rows start
+    // their device-to-host copy (second stream) while the next chunk is being shaded, so most of the PCIe time of the
+    // 12 B/pixel image hides behind the shade kernel.  Band rows [a, b) live at image rows [H - b, H - a) of the flipped
+    // Screen layout (screen.cpp:37-43): one contiguous range per chunk.
+    const int rows = c->y1 - c->y0;
+    const int chunks = out_rgb ? std::max(1, std::min(8, rows / 96)) : 1;
+    for (int k = 0; k < chunks; k++) {
+        const int a = c->y0 + (int)((long long)rows * k / chunks), b = c->y0 + (int)((long long)rows * (k + 1) / chunks);
+        FrameDev fr = c->fr; fr.y0 = a; fr.y1 = b;
+        launch_shade(c->stream, grid_for(c->W, b - a), kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, c->cur), (float*)c->rgb.p);
+        c->n_launches++;
+        RCHECK(c, cudaGetLastError());
+        if (out_rgb) {
+            RCHECK(c, cudaEventRecord(c->ev_chunk[k], c->stream));
+            RCHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k], 0));
+            const size_t off = (size_t)(c->H - b) * c->W * 3, cnt = (size_t)(b - a) * c->W * 3;
+            RCHECK(c, cudaMemcpyAsync(out_rgb + off, (const float*)c->rgb.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
     RCHECK(c, mark(c, 5, 0));
     RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
     int rc = capture_stage(c, ROMIS_PASS_FINAL, c->cur);
@@ -631,9 +670,7 @@ extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
     c->history_valid = true;
     c->in_frame = false;
     if (out_rgb) {
-        // band rows [y0, y1) live at image rows [H - y1, H - y0) of the flipped Screen layout: one contiguous range
-        size_t off = (size_t)(c->H - c->y1) * c->W * 3, cnt = (size_t)(c->y1 - c->y0) * c->W * 3;
-        RCHECK(c, cudaMemcpyAsync(out_rgb + off, (const float*)c->rgb.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RCHECK(c, cudaStreamSynchronize(c->copy_stream));
         RCHECK(c, cudaStreamSynchronize(c->stream));
     }
     return ROMIS_OK;

@@ -23,6 +23,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", "g++",
          "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+if os.environ.get("ROMIS_LEAF_MAX"):   # tuning knob, see bvh.cpp
+    FLAGS.append("-DROMIS_LEAF_MAX=" + os.environ["ROMIS_LEAF_MAX"])
 if os.environ.get("ROMIS_MINB"):       # tuning knob, see device_common.cuh
     FLAGS.append("-DROMIS_MINB=" + os.environ["ROMIS_MINB"])
 

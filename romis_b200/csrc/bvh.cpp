@@ -7,6 +7,12 @@
 #include <cstring>
 #include <numeric>
 
+// Triangles per leaf.  Measured on B200 (C2 1080p, tools/quick_bench.py): 2 beats 1, 4 and 8 -- a triangle test costs about
+// as much as a box pair, so small leaves win once the rays are incoherent (shadow rays).
+#ifndef ROMIS_LEAF_MAX
+#define ROMIS_LEAF_MAX 2
+#endif
+
 namespace romis {
 namespace {
 
@@ -28,7 +34,7 @@ struct Builder {
     std::vector<int> order;
     Bvh* out;
     float pad;
-    static constexpr int kLeafMax = 4;
+    static constexpr int kLeafMax = ROMIS_LEAF_MAX;
     static constexpr int kBins = 16;
 
     struct Ref { int32_t child; int32_t count; Box box; int depth; };

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from romis_b200 import abi
-from romis_b200.bands import band_rows, check_bands
+from romis_b200.bands import balanced_band_edges, band_rows, check_bands
 from romis_b200.scene import Camera, Features, LIGHT_DTYPE, Scene, synthetic_lights
 from cases import CASES
 from common import load_golden, load_scene
@@ -67,3 +67,24 @@ def test_band_partition():
     check_bands(1080, 8, 30)
     with pytest.raises(ValueError):
         check_bands(64, 8, 10)
+
+
+def test_equal_cost_band_edges():
+    """balanced_band_edges: contiguous, deterministic, each band >= min_rows, costs nearly equal."""
+    rng = np.random.default_rng(2)
+    for H, G, r in ((1080, 8, 10), (2160, 8, 30), (360, 2, 10), (97, 3, 7)):
+        cost = rng.uniform(0.0, 1.0, H) ** 3 * 1000 + 40.0
+        cost[: H // 5] = 40.0                         # a stretch of cheap (all-miss) rows
+        e = balanced_band_edges(cost, G, r)
+        assert e == balanced_band_edges(cost, G, r)
+        assert e[0] == 0 and e[-1] == H and len(e) == G + 1
+        sizes = np.diff(e)
+        assert (sizes >= r).all()
+        band_cost = np.add.reduceat(cost, e[:-1])
+        assert band_cost.max() <= band_cost.mean() * 1.25
+    # degenerate: everything in one row-range still leaves room for every band
+    cost = np.zeros(100); cost[95:] = 1.0
+    e = balanced_band_edges(cost, 4, 10)
+    assert (np.diff(e) >= 10).all() and e[-1] == 100
+    with pytest.raises(ValueError):
+        balanced_band_edges(np.ones(30), 4, 10)

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
     // Phase 1 -- pick the stream: k draws (x before y, always 2k draws, render_utils.cpp:109-110), clamp to the image, and in
     // biased mode apply the hard-coded depth / normal heuristics (:114-118).  Only the 16-byte {t, n} of each neighbour is
     // touched here and the iterations are independent, so their gathers overlap.  Self goes last (:124).
-    int stream[ROMIS_MAX_K + 1];        // packed (local row << 16 ... ) would cap W; keep two ints' worth in one: nrow * W + nx
+    uint32_t stream[ROMIS_MAX_K + 1];   // (local row << 16) | x  -- width and band height are validated to fit 16 bits
     int ns = 0;
     const float4 own_tn = g.tn[(size_t)lrow * fr.W + x];
     for (int nb = 0; nb < k; nb++) {
@@ -34,28 +34,28 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         int dy = romis_rng_uniform_int(romis_rng_bits(ek, 2u * nb + 1u), -rad, rad);
         int nx = min(max(x + dx, 0), fr.W - 1);
         int ny = min(max(y + dy, 0), fr.H - 1);
-        int nidx = (ny - fr.ey0) * fr.W + nx;
+        int nrow = ny - fr.ey0;
         bool keep = true;
         if (!UNBIASED) {
-            float4 ntn = g.tn[nidx];
+            float4 ntn = g.tn[(size_t)nrow * fr.W + nx];
             float depthFracDiff = fabsf(1.0f - (ntn.x / own_tn.x));
             float normalsDot = dot3(V3(ntn.y, ntn.z, ntn.w), V3(own_tn.y, own_tn.z, own_tn.w));
             keep = !(depthFracDiff > 0.1f || normalsDot < 0.90630778703f);
         }
-        if (keep) stream[ns++] = nidx;
+        if (keep) stream[ns++] = ((uint32_t)nrow << 16) | (uint32_t)nx;
     }
-    stream[ns++] = lrow * fr.W + x;
+    stream[ns++] = ((uint32_t)lrow << 16) | (uint32_t)x;
     // Phase 2 -- stream the selected reservoirs through Reservoir::update in order (reservoir.cpp:42-53); the records of
     // entry s+1 are fetched while entry s is being evaluated.
     uint4 rec[CAP], nrec[CAP]; uint32_t Mi[CAP], nMi[CAP];
     {
-        int srow = stream[0] / fr.W, sx = stream[0] - srow * fr.W;
+        int srow = (int)(stream[0] >> 16), sx = (int)(stream[0] & 0xffffu);
         ROMIS_FOR_SUB(j, NT, N) { nrec[j] = res_rec(in, srow, j)[sx]; nMi[j] = res_m(in, srow, j)[sx]; }
     }
     for (int s = 0; s < ns; s++) {
         ROMIS_FOR_SUB(j, NT, N) { rec[j] = nrec[j]; Mi[j] = nMi[j]; }
         if (s + 1 < ns) {
-            int srow = stream[s + 1] / fr.W, sx = stream[s + 1] - srow * fr.W;
+            int srow = (int)(stream[s + 1] >> 16), sx = (int)(stream[s + 1] & 0xffffu);
             ROMIS_FOR_SUB(j, NT, N) { nrec[j] = res_rec(in, srow, j)[sx]; nMi[j] = res_m(in, srow, j)[sx]; }
         }
         ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, rec[j], Mi[j], rk, rc);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         v3 spos[CAP], scol[CAP];
                 ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
         for (int s = 0; s < ns; s++) {
-            int srow = stream[s] / fr.W, sx = stream[s] - srow * fr.W;
+            int srow = (int)(stream[s] >> 16), sx = (int)(stream[s] & 0xffffu);
             int sy = srow + fr.ey0;
             PixCtx cs = make_ctx(sc, fr, g, sx, sy);
             uint64_t tot = 0;

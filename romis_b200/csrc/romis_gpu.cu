@@ -333,7 +333,7 @@ extern "C" int romis_set_stage_timing(romis_ctx* c, int on) { if (!c) return ROM
 
 static int validate(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H, const romis_rng* rng) {
     if (!f || !cam || !rng) return fail(c, ROMIS_ERR_INVALID, "null features / camera / rng");
-    if (W < 1 || H < 1 || (long long)W * H > 0x7fffffffLL) return fail(c, ROMIS_ERR_INVALID, "bad resolution");
+    if (W < 1 || H < 1 || W > 65535 || H > 65535) return fail(c, ROMIS_ERR_INVALID, "resolution must be 1..65535 in each dimension");
     if (f->numSamplesInReservoir < 1 || f->numSamplesInReservoir > 32) return fail(c, ROMIS_ERR_INVALID, "numSamplesInReservoir must be 1..32 (ui.cpp:305)");
     if (f->initialLightSamples < 1) return fail(c, ROMIS_ERR_INVALID, "initialLightSamples must be >= 1");
     if (f->numNeighboursToSample > ROMIS_MAX_K) return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample must be <= 32");

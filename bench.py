@@ -294,16 +294,31 @@ def main():
         if ms > 0:
             gbs = pb[name] * px / (ms * 1e-3) / 1e9
             per_pass[name] = {"ms_per_launch": round(ms, 4), "algorithmic_bytes_per_px": pb[name], "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    # DRAM traffic per launch from the committed ncu --set full capture of this same command (profiles/): only meaningful for
+    # the configuration and GPU count it was taken on
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("config") == args.config:
+            for name in per_pass:
+                k = tj["kernels"].get(name + "_kernel")
+                if k:
+                    per_pass[name]["dram_traffic_bytes"] = int(k["dram_bytes_read"] + k["dram_bytes_write"])
+                    per_pass[name]["algorithmic_bytes"] = int(pb[name] * px)
+                    per_pass[name]["ncu_warp_inst_per_cycle_per_sm_of_4"] = round(k["warp_inst_per_cycle_per_sm"], 2)
+                    traffic[name] = per_pass[name]["dram_traffic_bytes"]
     dominant = max(per_pass, key=lambda k: per_pass[k]["ms_per_launch"] * (stages.get("n_spatial", 1) if k == "spatial" else 1))
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": per_pass[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_pass[dominant]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": per_pass[dominant]["frac"], "traffic": traffic.get(dominant), "traffic_source": "profiles/r01c_summary.md (ncu --set full)" if traffic else None,
+                "peak_source": peak_src,
                 "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the pass kernels are issue-bound by the parity-exact fp32/fp64 arithmetic, see DESIGN.md",
                 "passes": per_pass}
     line = {"metric": "ReSTIR frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the step's events)",
-                       "sharding": (f"{world} row bands, halo = radius rows, " + ("pushed into peer-mapped (CUDA IPC) buffers over NVLink, flag-ordered" if args.halo == "peer" else "NCCL p2p")) if world > 1 else "single GPU",
+                       "sharding": (f"{world} row bands, halo = radius rows, " + ("pushed into peer-mapped (CUDA IPC) buffers over NVLink, flag-ordered" if br.transport == "peer" else "NCCL p2p" + (f" (peer mapping unavailable: {br.fallback_reason})" if br.fallback_reason else ""))) if world > 1 else "single GPU",
                        "band_edges": br.edges if br.edges is not None else "equal rows"},
             "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,

@@ -98,6 +98,7 @@ class BandedRenderer:
         self._height = None
         self.transport = transport if world_size > 1 else "none"
         self._attached = None
+        self.fallback_reason = None
         self.edges = None           # explicit band edges (balanced_band_edges); None = equal row counts
 
     def _attach_peers(self, features, W, H):
@@ -107,12 +108,34 @@ class BandedRenderer:
             return
         if self._attached is not None:
             self.r.peer_detach()
-        self.r.band_prepare(features, W, H)
+        ok, err = 1, ""
+        try:
+            self.r.band_prepare(features, W, H)
+            blob = self.r.peer_export()
+        except Exception as e:                          # noqa: BLE001 -- every rank must still reach the collectives below
+            ok, err, blob = 0, str(e), b""
         blobs = [None] * self.world_size
-        dist.all_gather_object(blobs, self.r.peer_export())
-        self.r.peer_attach(blobs[self.rank - 1] if self.rank > 0 else None,
-                           blobs[self.rank + 1] if self.rank < self.world_size - 1 else None)
-        dist.barrier()
+        dist.all_gather_object(blobs, blob)
+        if ok and all(blobs):
+            try:
+                self.r.peer_attach(blobs[self.rank - 1] if self.rank > 0 else None,
+                                   blobs[self.rank + 1] if self.rank < self.world_size - 1 else None)
+            except Exception as e:                      # noqa: BLE001
+                ok, err = 0, str(e)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            # some rank cannot map its neighbour (no peer access, IPC disabled, ...): everybody falls back to NCCL p2p
+            try:
+                self.r.peer_detach()
+            except Exception:                           # noqa: BLE001
+                pass
+            self.transport = "nccl"
+            self.fallback_reason = err or "a neighbouring rank could not attach"
+            self._attached = None
+            return
         self._attached = key
 
     def balance(self, camera, W: int, H: int, radius: int, miss_cost: float = 0.04):
@@ -179,7 +202,7 @@ class BandedRenderer:
         self.set_height(H, features.spatialResampleRadius if features.spatialReuse else 0)
         r = self.r
         if self.transport == "peer" and features.spatialReuse:
-            self._attach_peers(features, W, H)
+            self._attach_peers(features, W, H)          # may switch self.transport to "nccl" on every rank
         with torch.cuda.stream(self.stream):
             r.frame_begin(features, camera, W, H, history_valid, seed, frame)
             if features.spatialReuse:

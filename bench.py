@@ -60,7 +60,17 @@ def workload(name: str):
         s = Scene.load(os.path.join(SCENES, "CornellNightClub.npz"))
         return ("cornell-nightclub 3840x2160 M=32 N=2 temporal + 3 spatial k=5 r=10, visibility reuse", s, 3840, 2160,
                 Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), Camera())
+    if name == "c4":     # the 64-frame orbit: same as c2 with the camera moving every frame (see camera_for_frame)
+        label, s, W, H, f, cam = workload("c2")
+        return (label + ", camera orbiting 360 deg / 64 frames", s, W, H, f, cam)
     raise SystemExit(f"unknown config {name}")
+
+
+def camera_for_frame(config: str, cam: Camera, frame: int) -> Camera:
+    """BASELINE C4: rotation.y = 30 deg + 360 deg * f / 64 via Trackball::setCamera (SURVEY.md 8d); other configs: static."""
+    if config != "c4":
+        return cam
+    return Camera(cam.fov_deg, cam.distance, cam.look_at, (cam.rotation_deg[0], 30.0 + 360.0 * (frame % 64) / 64.0, cam.rotation_deg[2]))
 
 
 # algorithmic bytes per pixel per pass (SURVEY.md 8d): S = 20 B per sub-reservoir, G = 20 B per pixel
@@ -130,7 +140,7 @@ def run_reference(args, label, scene, W, H, feat, cam, rank, world):
     times = []
     for fr in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        ref.render_frame(feat, cam, w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+        ref.render_frame(feat, camera_for_frame(args.config, cam, fr), w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
         dt = time.perf_counter() - t0
         if fr >= args.warmup:
             times.append(dt)
@@ -236,7 +246,7 @@ def main():
                 ev0.record(br.stream)
             if upload_lights:
                 r.upload_lights(scene.lights)
-            br.render_frame(feat, cam, W, H, fr > 0, SEED, fr, out=host_out)
+            br.render_frame(feat, camera_for_frame(args.config, cam, fr), W, H, fr > 0, SEED, fr, out=host_out)
             with torch.cuda.stream(br.stream):
                 ev1.record(br.stream)
             ev1.synchronize()

@@ -12,8 +12,9 @@ Frame 0 has no temporal history, so warm-up frames establish it; every timed fra
          on the device.  For N > 1 the frame is split into N row bands, one process per GPU, reservoir halo rows
          exchanged over NCCL before each spatial pass; time = max over ranks; "scaling": "strong" (one frame).
   e2e    the same metric through the reference-facing call romis_render_frame with HOST buffers: per step the
-         scene's lights are re-uploaded (the reference reads scene.lights fresh every frame, light.cpp:46-66) and
-         the float RGB image is read back into pinned host memory, both inside the timed region.
+         scene's lights are handed over again (the reference reads scene.lights fresh every frame, light.cpp:46-66) with
+         one light edited, so the table is dirty and is re-packed and re-sent, and the float RGB image is read back into
+         pinned host memory, all inside the timed region.
   roofline / cpu_baseline: see DESIGN.md "measurement".
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/libromis_ref.so: the reference's
@@ -245,6 +246,8 @@ def main():
                 flush.fill_(i & 0xff)
                 ev0.record(br.stream)
             if upload_lights:
+                # a light edited every frame (as from the reference's UI): the table is dirty, so it is re-packed and re-sent
+                scene.lights["c0"][0, 0] = np.float32(0.65 + 1e-4 * (fr % 7))
                 r.upload_lights(scene.lights)
             br.render_frame(feat, camera_for_frame(args.config, cam, fr), W, H, fr > 0, SEED, fr, out=host_out)
             with torch.cuda.stream(br.stream):
@@ -332,7 +335,7 @@ def main():
                        "band_edges": br.edges if br.edges is not None else "equal rows"},
             "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(scene.lights.nbytes + 128),
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(6 * 16 * len(scene.lights) + 256),
                     "d2h_bytes_per_step": int(px * 12), "gcandidates_per_s": W * H * feat.initialLightSamples * e2e_fps / 1e9},
             "gpu_launches": int(launches_per_frame * args.steps),
             "clocks": clk, "roofline": roofline}

@@ -127,7 +127,9 @@ int romis_abi_version(void);
  * EmbreeInterface::initScene / changeScene (embree_interface.cpp:30-56).  Resets temporal history. */
 int romis_upload_scene(romis_ctx* ctx, const romis_mesh_desc* meshes, int n_meshes,
                        const romis_texture* textures, int n_textures);
-/* Uploads scene.lights (read fresh every frame by the reference, light.cpp:46-66; call when dirty). */
+/* Uploads scene.lights.  The reference reads them fresh every frame (light.cpp:46-66) and the UI edits them without
+ * notification, so call this every frame: an unchanged table is detected and costs no transfer.  Fewer lights than before
+ * drop the temporal history (it stores light indices). */
 int romis_upload_lights(romis_ctx* ctx, const romis_light* lights, int n_lights);
 
 /* ---- the frame ---- */

@@ -84,6 +84,7 @@ struct romis_ctx {
     // timing
     bool stage_timing = false;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<float4> light_shadow;   // host copy of the packed light table on the device (dirty tracking)
     void* light_stage = nullptr; size_t light_stage_bytes = 0;     // pinned staging of the packed light table
     cudaEvent_t ev_lights = nullptr; bool light_copy_pending = false;
     cudaStream_t copy_stream = nullptr;     // image read-back, overlapped with shading (romis_frame_end)
@@ -293,9 +294,19 @@ extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int 
     RCHECK(c, cudaSetDevice(c->device));
     for (int i = 0; i < n; i++)
         if (lights[i].type > ROMIS_LIGHT_PARALLELOGRAM) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: unknown light type");
-    // Called every frame by the drop-in (the reference re-reads scene.lights every frame): pack into a pinned staging
-    // buffer and copy on the context's stream, ordered before the next frame's kernels, without a host synchronisation.
-    const size_t bytes = 6 * sizeof(float4) * (size_t)std::max(1, n);
+    // Called every frame by the drop-in (the reference re-reads scene.lights every frame and the UI edits them without
+    // notification, ui.cpp:172-261), so dirty tracking lives here: the packed table is compared with the one on the
+    // device and an unchanged table costs no transfer.  A changed table is packed into a pinned staging buffer and copied
+    // on the context's stream, ordered before the next frame's kernels, without a host synchronisation.
+    const size_t count = 6 * (size_t)n;
+    std::vector<float4> packed(std::max<size_t>(6, count));
+    for (int i = 0; i < n; i++) pack_light(lights[i], &packed[6 * (size_t)i]);
+    if (c->sc.lights && c->sc.n_lights == n && c->light_shadow.size() == packed.size() &&
+        std::memcmp(c->light_shadow.data(), packed.data(), packed.size() * sizeof(float4)) == 0)
+        return ROMIS_OK;
+    // The history stores (light index, u, v): with fewer lights than before, stored indices could point past the table.
+    if (n < c->sc.n_lights) c->history_valid = false;
+    const size_t bytes = sizeof(float4) * packed.size();
     if (c->light_stage_bytes < bytes) {
         RCHECK(c, cudaStreamSynchronize(c->stream));
         if (c->light_stage) cudaFreeHost(c->light_stage);
@@ -306,11 +317,11 @@ extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int 
     } else if (c->light_copy_pending) {
         RCHECK(c, cudaEventSynchronize(c->ev_lights));      // the previous copy out of the staging buffer (long done)
     }
-    float4* rec = (float4*)c->light_stage;
-    for (int i = 0; i < n; i++) pack_light(lights[i], rec + 6 * (size_t)i);
-    RCHECK(c, cudaMemcpyAsync(c->lights.p, rec, 6 * sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    std::memcpy(c->light_stage, packed.data(), bytes);
+    RCHECK(c, cudaMemcpyAsync(c->lights.p, c->light_stage, bytes, cudaMemcpyHostToDevice, c->stream));
     RCHECK(c, cudaEventRecord(c->ev_lights, c->stream));
     c->light_copy_pending = true;
+    c->light_shadow.swap(packed);
     c->sc.lights = (const float4*)c->lights.p;
     c->sc.n_lights = n;
     return ROMIS_OK;

@@ -194,3 +194,25 @@ def test_error_paths(renderer):
         r.reservoirs(abi.ROMIS_PASS_FINAL)
     finally:
         r.close()
+
+
+def test_light_table_dirty_tracking(renderer, oracle_factory):
+    """romis_upload_lights every frame (as the drop-in does): an unchanged table is a no-op, a shorter table drops the
+    history (it stores light indices), after which the frame equals the oracle's history-free frame."""
+    scene = load_scene("CornellNightClub")
+    feat = Features(spatialResamplingPasses=1)
+    W, H = 48, 32
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    orc = oracle_factory(); orc.upload_scene(scene); orc.reset_history()
+    renderer.upload_scene(scene); renderer.reset_history()
+    for fr in range(2):
+        renderer.upload_lights(scene.lights)                      # unchanged: must not disturb anything
+        oimg = orc.render_frame(feat, cam, W, H, fr > 0, 8, fr)
+        gimg = renderer.render_frame(feat, cam, W, H, fr > 0, 8, fr)
+        assert_bits_equal(gimg, oimg, f"frame {fr}")
+    fewer = scene.lights[:100].copy()
+    renderer.upload_lights(fewer); orc.upload_lights(fewer)
+    oimg = orc.render_frame(feat, cam, W, H, False, 8, 2)         # the reference would keep stale samples; we restart
+    gimg = renderer.render_frame(feat, cam, W, H, True, 8, 2)
+    assert_bits_equal(gimg, oimg, "frame after the light table shrank")
+    compare_stage("lights", "after shrink", renderer.reservoirs(abi.ROMIS_PASS_FINAL), orc.reservoirs(abi.ROMIS_PASS_FINAL))

@@ -167,9 +167,13 @@ int romis_frame_begin(romis_ctx* ctx, const romis_features* features, const romi
                       int width, int height, int history_valid, const romis_rng* rng);
 int romis_frame_spatial_pass(romis_ctx* ctx, int pass);
 int romis_frame_end(romis_ctx* ctx, float* out_rgb);
-/* Halo rows of the reservoir buffer the NEXT spatial pass reads.  which: 0 = send to the band above
- * (my first `radius` rows... in +y order: rows y0 .. y0+r), 1 = send to the band below (rows y1-r .. y1),
- * 2 = receive from the band above... see DESIGN.md "row bands".  Regions are contiguous device memory. */
+/* Halo rows (r = spatialResampleRadius) of the reservoir buffer the NEXT spatial pass reads, as contiguous device ranges:
+ *   ROMIS_HALO_SEND_LOW   my rows [y0, y0 + r)      -> to the band below (smaller y), its ROMIS_HALO_RECV_HIGH
+ *   ROMIS_HALO_SEND_HIGH  my rows [y1 - r, y1)      -> to the band above, its ROMIS_HALO_RECV_LOW
+ *   ROMIS_HALO_RECV_LOW   rows [max(0, y0 - r), y0)    <- from the band below
+ *   ROMIS_HALO_RECV_HIGH  rows [y1, min(H, y1 + r))    <- from the band above
+ * A range is empty (bytes = 0) at the image border.  Valid between romis_frame_begin and romis_frame_end; re-query
+ * before every pass (the buffers ping-pong). */
 enum { ROMIS_HALO_SEND_LOW = 0, ROMIS_HALO_SEND_HIGH = 1, ROMIS_HALO_RECV_LOW = 2, ROMIS_HALO_RECV_HIGH = 3 };
 int romis_halo_region(romis_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
 /* CUDA stream (cudaStream_t) the context launches on, so the caller can order its transport. */

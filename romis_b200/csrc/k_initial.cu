@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_ENGINE);
     romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
-        ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;               // light.cpp:58-60
+    ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;               // light.cpp:58-60
     const float invPdf = 1.0f / (float)sc.n_lights;                                 // light.cpp:80
     const uint32_t Mcand = fr.f.initialLightSamples;
     for (uint32_t i = 0; i < Mcand; i++) {
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     // light.cpp:85-95: visibility reuse zeroes W of occluded samples, otherwise W = (1/pdf)(1/M)wSum
     res_finish(r, N, sc, c, es);
     if (fr.f.initialSamplesVisibilityCheck) {
-                ROMIS_FOR_SUB(j, NT, N) {
+        ROMIS_FOR_SUB(j, NT, N) {
             v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
             if (!visible(sc, c, pos)) r.W[j] = 0.0f;
         }

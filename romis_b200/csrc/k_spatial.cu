@@ -67,20 +67,20 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         // reservoir.cpp:84-103: Z_j = sum of totalM(s) over stream reservoirs s whose OWN pixel sees y_j with pdf > 0
         uint64_t Z[CAP];
         v3 spos[CAP], scol[CAP];
-                ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
+        ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
         for (int s = 0; s < ns; s++) {
             int srow = (int)(stream[s] >> 16), sx = (int)(stream[s] & 0xffffu);
             int sy = srow + fr.ey0;
             PixCtx cs = make_ctx(sc, fr, g, sx, sy);
             uint64_t tot = 0;
-                        ROMIS_FOR_SUB(j, NT, N) tot += res_m(in, srow, j)[sx];
-                        ROMIS_FOR_SUB(j, NT, N) {
+            ROMIS_FOR_SUB(j, NT, N) tot += res_m(in, srow, j)[sx];
+            ROMIS_FOR_SUB(j, NT, N) {
                 float pdf = target_pdf(cs, es, spos[j], scol[j]);
                 // reservoir.cpp:89-92: pdf *= visibility; pdf > 0 counts.  The ray only matters when pdf > 0.
                 if (pdf > 0.0f && (!fr.f.spatialReuseVisibilityCheck || visible(sc, cs, spos[j]))) Z[j] += tot;
             }
         }
-                ROMIS_FOR_SUB(j, NT, N) {
+        ROMIS_FOR_SUB(j, NT, N) {
             float pdf = target_pdf(c, es, spos[j], scol[j]);
             r.W[j] = (pdf == 0.0f || Z[j] == 0ull) ? 0.0f : (1.0f / pdf) * (1.0f / (float)Z[j]) * r.wSum[j];
         }

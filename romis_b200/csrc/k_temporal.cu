@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
     constexpr int CAP = SubRes<NT>::CAP;
     uint4 crec[CAP], prec[CAP]; uint32_t cM[CAP], pM[CAP];
     uint64_t curTotal = 0, prevTotal = 0;
-        ROMIS_FOR_SUB(j, NT, N) {
+    ROMIS_FOR_SUB(j, NT, N) {
         crec[j] = res_rec(cur, lrow, j)[x]; cM[j] = res_m(cur, lrow, j)[x];
         prec[j] = res_rec(prev, lrow, j)[x]; pM[j] = res_m(prev, lrow, j)[x];
         curTotal += cM[j]; prevTotal += pM[j];
@@ -28,13 +28,13 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
     uint64_t cap = (uint64_t)fr.f.temporalClampM * curTotal + 1ull;
     if (prevTotal > cap) {
         uint32_t cap32 = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap;
-                ROMIS_FOR_SUB(j, NT, N) { if (pM[j] != 0u) pM[j] = cap32; }
+        ROMIS_FOR_SUB(j, NT, N) { if (pM[j] != 0u) pM[j] = cap32; }
     }
     PixCtx c = make_ctx(sc, fr, g, x, y);
     romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_TEMPORAL, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
     SubRes<NT> r; res_init(r, N);
-        ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, crec[j], cM[j], rk, rc);    // :169 current first
+    ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, crec[j], cM[j], rk, rc);    // :169 current first
         ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, prec[j], pM[j], rk, rc);    // then the predecessor
     res_take_counts(r, N);
     res_finish(r, N, sc, c, es);

@@ -1,19 +1,13 @@
-// reservoir.cuh -- register-resident sub-reservoirs shared by the pass kernels; one kernel per pass of the ReSTIR frame (renderReSTIR, reference src/rendering/render.cpp:28-62).
+// reservoir.cuh -- the per-pixel multi-sample reservoir of the reference (Reservoir, src/rendering/reservoir.h:28-73) as
+// register-resident state shared by the pass kernels: init, update, finish (W), store, and one stream entry of combine*.
 //
-//   primary_kernel   genPrimaryRayHits      (src/rendering/render_utils.cpp:13-34)   -> G-buffer
-//   initial_kernel   genInitialSamples      (render_utils.cpp:36-52, src/scene/light.cpp:39-99) + visibility reuse
-//   temporal_kernel  temporalReuse          (render_utils.cpp:142-177)
-//   spatial_kernel   spatialReuse, one pass (render_utils.cpp:87-140), biased or unbiased
-//   shade_kernel     final shading loop     (render.cpp:45-57, render_utils.cpp:54-65, tone_mapping.cpp:8-11, screen.cpp:37-43)
+// One thread owns one pixel: the weighted-reservoir stream of a pixel is sequential by definition (every update's accept
+// test depends on the running wSum, reservoir.cpp:22-25), and with >= 2 M pixels per frame the grid is wide enough
+// without intra-pixel parallelism (DESIGN.md 4 on why splitting a pixel over lanes does not pay).  Random draws are
+// addressed by (pixel, stage, stream, counter) (include/romis_rng.h), so results do not depend on launch shape or bands.
 //
-// One thread owns one pixel: the weighted-reservoir stream of a pixel is sequential by definition
-// (every update's accept test depends on the running wSum, reservoir.cpp:22-25), and with >= 2 M pixels
-// per frame the grid is wide enough that no intra-pixel parallelism is needed.  Random draws are
-// addressed by (pixel, stage, stream, counter) (include/romis_rng.h), so the result does not depend on
-// the launch shape, the band split or the pass order of other pixels.
-//
-// NT > 0: numSamplesInReservoir is the compile-time constant NT and sub-reservoirs live in registers.
-// NT == 0: runtime N <= 32, sub-reservoirs in local memory (generic fallback).
+// NT > 0: numSamplesInReservoir is the compile-time constant NT and sub-reservoirs live in registers (predicated writes
+// instead of dynamic indexing).  NT == 0: runtime N <= 32, sub-reservoirs in local memory (generic fallback).
 #pragma once
 #include "device_common.cuh"
 
@@ -92,7 +86,7 @@ template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, i
 
 // sampleNums = routed sums of the sources' M (reservoir.cpp:54,82); saturates at 2^32-1
 template <int NT> __device__ __forceinline__ void res_take_counts(SubRes<NT>& r, int N) {
-        ROMIS_FOR_SUB(j, NT, N) r.M[j] = r.cnt[j] > 0xffffffffull ? 0xffffffffu : (uint32_t)r.cnt[j];
+    ROMIS_FOR_SUB(j, NT, N) r.M[j] = r.cnt[j] > 0xffffffffull ? 0xffffffffu : (uint32_t)r.cnt[j];
 }
 
 }  // namespace romis

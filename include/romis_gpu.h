@@ -95,6 +95,19 @@ typedef struct romis_features {
     float exposure;                         /* common.h:136 */
 } romis_features;
 
+/* ---- R-MIS (renderRMIS, reference src/rendering/render.cpp:64-119): the fields of Features only that mode reads ---- */
+enum { ROMIS_MIS_EQUAL = 0, ROMIS_MIS_BALANCE = 1 };                                /* MISWeightRMIS, common.h:31-34 */
+enum { ROMIS_NEIGHBOURS_RANDOM = 0, ROMIS_NEIGHBOURS_SIMILAR = 1, ROMIS_NEIGHBOURS_DISSIMILAR = 2,
+       ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR = 3 };                             /* NeighbourSelectionStrategy, common.h:36-41 */
+typedef struct romis_rmis_params {
+    uint32_t maxIterationsMIS;                          /* common.h:116 */
+    uint32_t misWeightRMIS;                             /* common.h:118 */
+    uint32_t neighbourSelectionStrategy;                /* common.h:117 */
+    uint32_t neighbourSameGeometry;                     /* common.h:111 */
+    float neighbourMaxDepthDifferenceFraction;          /* common.h:112 */
+    float neighbourMaxNormalAngleDifferenceRadians;     /* common.h:113 (compared against the normals' dot product as is, neighbour_selection.cpp:18) */
+} romis_rmis_params;
+
 /* Camera: what Trackball::generateRay needs (reference framework/src/trackball.cpp:75-78,105-114).
  * origin = Trackball::position(); quat = glm::quat(rotationEulerAngles) as (w, x, y, z);
  * half_height = tan(fovy/2), half_width = aspect * half_height (trackball.cpp:26-27). */
@@ -150,6 +163,19 @@ int romis_render_frame_device(romis_ctx* ctx, const romis_features* features, co
                               int width, int height, int history_valid, const romis_rng* rng,
                               const float** dev_rgb);
 int romis_synchronize(romis_ctx* ctx);
+
+/* One R-MIS frame = renderRMIS (render.cpp:64-119): primary hits, a neighbour index grid (k neighbours per pixel within the
+ * spatial radius: random, or chosen by similarity of depth / normal / geometry, neighbour_selection.cpp), then
+ * maxIterationsMIS rounds of { initial RIS per pixel; every pixel shades the samples of its k+1 neighbourhood pixels with
+ * equal or balance-heuristic MIS weights and a shadow ray each }, averaged and tone mapped (combineToScreen,
+ * render_utils.cpp:68-85).  No temporal state.  Whole frame on one context (bands are not supported for this mode).
+ * ROMIS_NEIGHBOURS_DISSIMILAR is rejected: the reference passes a negative count to std::sample there
+ * (neighbour_selection.cpp:88-93), which is undefined behaviour. */
+int romis_render_frame_rmis(romis_ctx* ctx, const romis_features* features, const romis_rmis_params* rmis,
+                            const romis_camera* camera, int width, int height, const romis_rng* rng, float* out_rgb);
+/* Parity read-back of the last R-MIS frame's neighbour grid: xy[H][W][k+1][2] (entry 0 is the pixel itself, unused
+ * entries are -1) and count[H][W]. */
+int romis_download_rmis_neighbours(romis_ctx* ctx, int32_t* xy, uint32_t* count);
 
 /* ---- row-band sharding (one context per GPU) ---- */
 /* This context renders rows [y0, y1) of the height passed to the frame calls.  Pixels, RNG keys and

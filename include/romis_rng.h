@@ -39,7 +39,10 @@
 #define ROMIS_RNG_HD static inline
 #endif
 
-enum { ROMIS_STAGE_INITIAL = 0, ROMIS_STAGE_TEMPORAL = 1, ROMIS_STAGE_SPATIAL0 = 2 };
+enum { ROMIS_STAGE_INITIAL = 0, ROMIS_STAGE_TEMPORAL = 1, ROMIS_STAGE_SPATIAL0 = 2 /* + pass, < 64 */,
+       /* R-MIS (renderRMIS, reference src/rendering/render.cpp:64-119) */
+       ROMIS_STAGE_RMIS_NEIGH = 64,         /* neighbour index grid: ENGINE c = running count of engine calls of the pixel */
+       ROMIS_STAGE_RMIS_INITIAL0 = 128      /* + iteration: genInitialSamples of that iteration, counters as ROMIS_STAGE_INITIAL */ };
 enum { ROMIS_STREAM_ENGINE = 0, ROMIS_STREAM_RAND = 1 };
 
 /* 32-bit finaliser (two odd multipliers, three xorshifts) */

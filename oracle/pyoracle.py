@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 from romis_b200 import abi
-from romis_b200.scene import Camera, Features, Scene, LIGHT_DTYPE, VERTEX_DTYPE, Mesh
+from romis_b200.scene import Camera, Features, RmisParams, Scene, LIGHT_DTYPE, VERTEX_DTYPE, Mesh
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
@@ -141,6 +141,19 @@ class Oracle:
                                               out.ctypes.data if want_image else None))
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         return out
+
+    def render_frame_rmis(self, features: Features, rmis: RmisParams, camera: abi.romis_camera, W: int, H: int, seed: int, frame: int):
+        """renderRMIS restated (oracle/restir_oracle.c orc_render_frame_rmis).  Returns (image, neighbour xy, counts)."""
+        f = features.to_abi(); rp = rmis.to_abi(); r = abi.romis_rng(seed, frame, 0)
+        K1 = features.numNeighboursToSample + 1
+        img = np.zeros((H, W, 3), np.float32); xy = np.full((H, W, K1, 2), -1, np.int32); cnt = np.zeros((H, W), np.uint32)
+        self.lib.orc_render_frame_rmis.argtypes = [C.c_void_p, C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params),
+                                                   C.POINTER(abi.romis_camera), C.c_int, C.c_int, C.POINTER(abi.romis_rng),
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.orc_render_frame_rmis(self.ctx, C.byref(f), C.byref(rp), C.byref(camera), W, H, C.byref(r),
+                                                   img.ctypes.data, xy.ctypes.data, cnt.ctypes.data))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        return img, xy, cnt
 
     def reservoirs(self, pass_id: int) -> ReservoirState:
         st = ReservoirState(self.N, self.H, self.W)
@@ -274,6 +287,20 @@ class RefLib:
 
     def reset_history(self):
         self.lib.ref_reset_history()
+
+    def render_frame_rmis(self, features: Features, rmis: RmisParams, camera: Camera, W: int, H: int, seed: int, frame: int,
+                          want_neighbours: bool = True):
+        """renderRMIS (reference src/rendering/render.cpp:64-119), called whole.  Returns (image, neighbour xy, counts)."""
+        f = features.to_abi(); rp = rmis.to_abi(); r = abi.romis_rng(seed, frame, 0); cd = self._cam(camera)
+        K1 = features.numNeighboursToSample + 1
+        img = np.zeros((H, W, 3), np.float32)
+        xy = np.full((H, W, K1, 2), -1, np.int32) if want_neighbours else None
+        cnt = np.zeros((H, W), np.uint32) if want_neighbours else None
+        self.lib.ref_render_frame_rmis.argtypes = [C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params), C.POINTER(_ref_camera_desc),
+                                                   C.c_int, C.c_int, C.POINTER(abi.romis_rng), C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.ref_render_frame_rmis(C.byref(f), C.byref(rp), C.byref(cd), W, H, C.byref(r), img.ctypes.data,
+                                                   xy.ctypes.data if want_neighbours else None, cnt.ctypes.data if want_neighbours else None))
+        return img, xy, cnt
 
     def render_frame(self, features: Features, camera: Camera, W: int, H: int, history_valid: bool, seed: int, frame: int,
                      flags: int = 0, dump: bool = True, want_image: bool = True) -> RefFrame:

@@ -14,6 +14,7 @@
 #include <framework/window.h>
 #include <post_processing/tone_mapping.h>
 #include <rendering/render.h>
+#include <rendering/neighbour_selection.h>
 #include <rendering/render_utils.h>
 #include <rendering/reservoir.h>
 #include <rendering/screen.h>
@@ -234,6 +235,60 @@ int ref_make_camera(const ref_camera_desc* c, int width, int height, romis_camer
 }
 
 int ref_reset_history(void) { g_prev.reset(); return 0; }
+
+// renderRMIS itself (reference src/rendering/render.cpp:64-119), called whole; the neighbour index grid is additionally
+// produced by a separate call of generateResampleIndicesGrid under the same random-stream keys so that it can be dumped.
+int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
+                          const romis_rng* rng, float* out_rgb, int32_t* neigh_xy, uint32_t* neigh_count) {
+    if (!g_embree) { g_err = "no scene"; return -1; }
+    try {
+        Features features = toFeatures(*f);
+        features.rayTraceMode = RayTraceMode::RMIS;
+        features.maxIterationsMIS = rp->maxIterationsMIS;
+        features.misWeightRMIS = static_cast<MISWeightRMIS>(rp->misWeightRMIS);
+        features.neighbourSelectionStrategy = static_cast<NeighbourSelectionStrategy>(rp->neighbourSelectionStrategy);
+        features.neighbourSameGeometry = rp->neighbourSameGeometry != 0;
+        features.neighbourMaxDepthDifferenceFraction = rp->neighbourMaxDepthDifferenceFraction;
+        features.neighbourMaxNormalAngleDifferenceRadians = rp->neighbourMaxNormalAngleDifferenceRadians;
+        Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
+        Screen screen(glm::ivec2(W, H), false);
+        Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
+        camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
+        ShimState& s = g_shim;
+        s.mode = SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
+        s.N = (int)features.numSamplesInReservoir; s.k = (int)features.numNeighboursToSample;
+#ifdef _OPENMP
+        omp_set_num_threads(1);
+#endif
+        NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);
+        const uint32_t K1 = features.numNeighboursToSample + 1U;
+        if (neigh_xy || neigh_count) {
+            s.stage_queue = { SHIM_STAGE_PRIMARY_THEN_NEIGH }; s.stage_pos = 0; s.stage = SHIM_STAGE_NONE;
+            PrimaryHitGrid primaryHits = genPrimaryRayHits(g_scene, camera, *g_embree, screen, features);
+            ResampleIndicesGrid grid = generateResampleIndicesGrid(primaryHits, screen.resolution(), features);
+            for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+                const auto& v = grid[y][x]; size_t p = size_t(y) * W + x;
+                if (neigh_count) neigh_count[p] = (uint32_t)v.size();
+                if (neigh_xy) for (uint32_t i = 0; i < K1; i++) {
+                    neigh_xy[(p * K1 + i) * 2 + 0] = i < v.size() ? v[i].x : -1;
+                    neigh_xy[(p * K1 + i) * 2 + 1] = i < v.size() ? v[i].y : -1;
+                }
+            }
+        }
+        s.stage_queue.clear(); s.stage_pos = 0; s.stage = SHIM_STAGE_NONE;
+        s.stage_queue.push_back(SHIM_STAGE_PRIMARY_THEN_NEIGH);                         // genPrimaryRayHits, then the index grid
+        for (uint32_t it = 0; it < features.maxIterationsMIS; it++) {
+            s.stage_queue.push_back(ROMIS_STAGE_RMIS_INITIAL0 + (int)it);               // genInitialSamples
+            s.stage_queue.push_back(SHIM_STAGE_NONE);                                   // the gather loop's bar (render.cpp:75)
+        }
+        s.stage_queue.push_back(SHIM_STAGE_NONE);                                       // combineToScreen
+        renderRMIS(g_scene, camera, *g_embree, screen, features);
+        std::cout.rdbuf(old);
+        if (s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
+        if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    return 0;
+}
 
 #ifdef ROMIS_WITH_DROPIN
 }  // extern "C"

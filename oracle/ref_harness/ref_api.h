@@ -48,6 +48,8 @@ int ref_texture_data(int i, float* px);
 int ref_lights_data(romis_light* out);
 int ref_make_camera(const ref_camera_desc* c, int width, int height, romis_camera* out);
 int ref_reset_history(void);
+int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
+                          const romis_rng* rng, float* out_rgb, int32_t* neigh_xy, uint32_t* neigh_count);
 int ref_num_threads(void);
 int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
                      const romis_rng* rng, int flags, ref_frame_dump* dump, float* out_rgb, ref_timings* tm);

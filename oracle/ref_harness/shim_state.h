@@ -4,7 +4,8 @@
 #include <vector>
 
 enum ShimMode { SHIM_PARITY = 0, SHIM_TIMING = 1 };
-enum { SHIM_STAGE_NONE = -1 };      // stages without draws: primary rays, final shading
+enum { SHIM_STAGE_NONE = -1,        // stages without draws: primary rays, final shading
+       SHIM_STAGE_PRIMARY_THEN_NEIGH = -2 };   // renderRMIS: primary rays, then the neighbour index grid (no bar of its own)
 
 struct ShimState {
     int mode = SHIM_PARITY;

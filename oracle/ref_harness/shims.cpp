@@ -61,21 +61,31 @@ extern "C" void romis_shim_row_done(void) {
     s.rows_done++;
 }
 
+// stages in which the reference constructs one std::mt19937 per pixel (genCanonicalSamples, light.cpp:49-50; the R-MIS
+// neighbour selection, neighbour_selection.cpp:28-29,72-73): the constructor marks the pixel boundary
+static bool per_pixel_engine_stage(int stage) {
+    return stage == ROMIS_STAGE_INITIAL || stage == ROMIS_STAGE_RMIS_NEIGH ||
+           (stage >= ROMIS_STAGE_RMIS_INITIAL0 && stage < ROMIS_STAGE_RMIS_INITIAL0 + 64);
+}
+
 extern "C" void romis_shim_engine_ctor(void) {
     ShimState& s = g_shim;
     if (s.mode != SHIM_PARITY) return;
-    if (s.stage == ROMIS_STAGE_INITIAL) { s.pixel++; s.engine_ctr = 0; s.rand_ctr = 0; }
+    // renderRMIS builds its neighbour index grid right after the primary rays without a progress bar of its own
+    // (render.cpp:68-69): the first engine constructed in that gap opens the neighbour-selection stage
+    if (s.stage == SHIM_STAGE_PRIMARY_THEN_NEIGH) { s.stage = ROMIS_STAGE_RMIS_NEIGH; s.pixel = -1; }
+    if (per_pixel_engine_stage(s.stage)) { s.pixel++; s.engine_ctr = 0; s.rand_ctr = 0; }
 }
 
 extern "C" uint32_t romis_shim_engine_next(void) {
     ShimState& s = g_shim;
     if (s.mode != SHIM_PARITY) return fast_next();
-    if (s.stage == ROMIS_STAGE_INITIAL) {
+    if (per_pixel_engine_stage(s.stage)) {
         if (s.pixel < 0 || s.pixel >= (long)s.W * s.H) shim_fail("engine draw outside a pixel");
         romis_stream_key k = romis_rng_stream(s.seed, s.frame, (uint32_t)s.stage, (uint32_t)s.pixel, ROMIS_STREAM_ENGINE);
         return romis_rng_bits(k, s.engine_ctr++);
     }
-    if (s.stage >= ROMIS_STAGE_SPATIAL0) {
+    if (s.stage >= ROMIS_STAGE_SPATIAL0 && s.stage < ROMIS_STAGE_RMIS_NEIGH) {
         if (s.k <= 0) shim_fail("engine draw with k == 0");
         long pix = s.engine_total / (2L * s.k);
         uint32_t c = (uint32_t)(s.engine_total % (2L * s.k));
@@ -93,11 +103,11 @@ extern "C" int rand(void) {
     ShimState& s = g_shim;
     if (s.mode != SHIM_PARITY) return int(fast_next() >> 1);
     long pix; uint32_t c;
-    if (s.stage == ROMIS_STAGE_INITIAL) {
+    if (per_pixel_engine_stage(s.stage)) {
         pix = s.pixel; c = s.rand_ctr++;
     } else if (s.stage == ROMIS_STAGE_TEMPORAL) {
         pix = s.rand_total / (2L * s.N); c = (uint32_t)(s.rand_total % (2L * s.N)); s.rand_total++;
-    } else if (s.stage >= ROMIS_STAGE_SPATIAL0) {
+    } else if (s.stage >= ROMIS_STAGE_SPATIAL0 && s.stage < ROMIS_STAGE_RMIS_NEIGH) {
         if (s.k > 0) { pix = s.pixel; c = s.rand_ctr++; }
         else { pix = s.rand_total / s.N; c = (uint32_t)(s.rand_total % s.N); s.rand_total++; }
     } else { shim_fail("rand() in a stage that has none"); return 0; }

@@ -176,12 +176,12 @@ static uint64_t total_m(const orc_sub* r, int N) { uint64_t s = 0; for (int j = 
 static v3 lv(const float* p) { return V3(p[0], p[1], p[2]); }
 
 /* genCanonicalSamples (src/scene/light.cpp:39-99) with the samplers of light.cpp:19-34 */
-static void gen_canonical(const orc_env* e, const romis_rng* rng, uint32_t pixel, v3 dir, const orc_hit* h, orc_sub* r) {
+static void gen_canonical(const orc_env* e, const romis_rng* rng, uint32_t stage, uint32_t pixel, v3 dir, const orc_hit* h, orc_sub* r) {
     const orc_ctx* c = e->c; const romis_features* f = e->f; const int N = c->N;
     reservoir_init(r, N);                                                       /* :41 */
     if (c->nlights == 0) return;                                                /* :46 */
-    romis_stream_key ek = romis_rng_stream(rng->seed, rng->frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_ENGINE);
-    romis_stream_key rk = romis_rng_stream(rng->seed, rng->frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_RAND);
+    romis_stream_key ek = romis_rng_stream(rng->seed, rng->frame, stage, pixel, ROMIS_STREAM_ENGINE);
+    romis_stream_key rk = romis_rng_stream(rng->seed, rng->frame, stage, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
     for (int j = 0; j < N; j++) r[j].M = 0;                                     /* :58-60 */
     for (uint32_t i = 0; i < f->initialLightSamples; i++) {                     /* :63 */
@@ -341,6 +341,28 @@ int orc_upload_lights(orc_ctx* c, const romis_light* lights, int n) {
 
 int orc_reset_history(orc_ctx* c) { c->have_prev = 0; return 0; }
 
+/* genPrimaryRayHits (src/rendering/render_utils.cpp:13-34) -> closestHit (embree_interface.cpp:64-90) */
+static void primary_hits(orc_ctx* c, const romis_camera* cam, v3 origin, int W, int H) {
+    #pragma omp parallel for schedule(guided)
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        orc_hit* h = &c->gbuf[(size_t)y * W + x];
+        v3 d = gen_ray_dir(cam, x, y, W, H);
+        float o[3] = {origin.x, origin.y, origin.z}, dd[3] = {d.x, d.y, d.z};
+        float t, u, v; uint32_t tri;
+        if (otr_closest(c->tracer, o, dd, FLT_MAX, &t, &u, &v, &tri)) {
+            const romis_vertex* a = &c->tri_verts[3 * tri];
+            float w = (1.0f - u) - v;           /* attribute interpolation: (w*a + u*b) + v*c (tracer.h) */
+            h->t = t;
+            h->n = add3(add3(scale3(lv(a[0].normal), w), scale3(lv(a[1].normal), u)), scale3(lv(a[2].normal), v));
+            h->uv[0] = (w * a[0].texcoord[0] + u * a[1].texcoord[0]) + v * a[2].texcoord[0];
+            h->uv[1] = (w * a[0].texcoord[1] + u * a[1].texcoord[1]) + v * a[2].texcoord[1];
+            h->mesh = c->tri_mesh[tri];
+        } else {                                /* hitInfo untouched, ray.t = FLT_MAX (SURVEY A.4) */
+            h->t = FLT_MAX; h->n = V3(0, 0, 0); h->uv[0] = h->uv[1] = 0.0f; h->mesh = (uint32_t)c->nmesh;
+        }
+    }
+}
+
 /* renderReSTIR (src/rendering/render.cpp:28-62) */
 int orc_render_frame(orc_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H, int history_valid,
                      const romis_rng* rng, float* out_rgb) {
@@ -362,31 +384,14 @@ int orc_render_frame(orc_ctx* c, const romis_features* f, const romis_camera* ca
     const int k = (int)f->numNeighboursToSample, r = (int)f->spatialResampleRadius;
     if (k > 64) { strcpy(c->err, "numNeighboursToSample > 64"); return ROMIS_ERR_INVALID; }
 
-    /* 1. genPrimaryRayHits (src/rendering/render_utils.cpp:13-34) -> closestHit (embree_interface.cpp:64-90) */
-    #pragma omp parallel for schedule(guided)
-    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
-        orc_hit* h = &c->gbuf[(size_t)y * W + x];
-        v3 d = gen_ray_dir(cam, x, y, W, H);
-        float o[3] = {env.origin.x, env.origin.y, env.origin.z}, dd[3] = {d.x, d.y, d.z};
-        float t, u, v; uint32_t tri;
-        if (otr_closest(c->tracer, o, dd, FLT_MAX, &t, &u, &v, &tri)) {
-            const romis_vertex* a = &c->tri_verts[3 * tri];
-            float w = (1.0f - u) - v;           /* attribute interpolation: (w*a + u*b) + v*c (tracer.h) */
-            h->t = t;
-            h->n = add3(add3(scale3(lv(a[0].normal), w), scale3(lv(a[1].normal), u)), scale3(lv(a[2].normal), v));
-            h->uv[0] = (w * a[0].texcoord[0] + u * a[1].texcoord[0]) + v * a[2].texcoord[0];
-            h->uv[1] = (w * a[0].texcoord[1] + u * a[1].texcoord[1]) + v * a[2].texcoord[1];
-            h->mesh = c->tri_mesh[tri];
-        } else {                                /* hitInfo untouched, ray.t = FLT_MAX (SURVEY A.4) */
-            h->t = FLT_MAX; h->n = V3(0, 0, 0); h->uv[0] = h->uv[1] = 0.0f; h->mesh = (uint32_t)c->nmesh;
-        }
-    }
+    /* 1. genPrimaryRayHits */
+    primary_hits(c, cam, env.origin, W, H);
 
     /* 2. genInitialSamples (render_utils.cpp:36-52) */
     #pragma omp parallel for schedule(guided)
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
         size_t p = (size_t)y * W + x;
-        gen_canonical(e, rng, (uint32_t)p, gen_ray_dir(cam, x, y, W, H), &c->gbuf[p], &c->cur[p * N]);
+        gen_canonical(e, rng, ROMIS_STAGE_INITIAL, (uint32_t)p, gen_ray_dir(cam, x, y, W, H), &c->gbuf[p], &c->cur[p * N]);
     }
     snapshot(c, 0);
 
@@ -480,6 +485,194 @@ int orc_render_frame(orc_ctx* c, const romis_features* f, const romis_camera* ca
     /* the returned grid becomes next frame's previousFrameGrid (main.cpp:165) */
     orc_sub* t = c->prev; c->prev = c->cur; c->cur = t;
     c->have_prev = 1;
+    return 0;
+}
+
+
+/* =============================================================================================== */
+/* R-MIS (renderRMIS, src/rendering/render.cpp:64-119)                                              */
+/* =============================================================================================== */
+#define ORC_MAX_K 32
+
+/* libstdc++ 13 uniform_int_distribution on a 32-bit engine: Lemire's method WITH its rejection step
+ * (/usr/include/c++/13/bits/uniform_int_dist.h:255-281), as std::sample instantiates it inside the reference
+ * (neighbour_selection.cpp:79-103).  Returns a value in [0, range). */
+static uint32_t lemire32(romis_stream_key ek, uint32_t* ec, uint32_t range) {
+    uint64_t product = (uint64_t)romis_rng_bits(ek, (*ec)++) * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+        uint32_t threshold = (0u - range) % range;
+        while (low < threshold) { product = (uint64_t)romis_rng_bits(ek, (*ec)++) * (uint64_t)range; low = (uint32_t)product; }
+    }
+    return (uint32_t)(product >> 32);
+}
+
+/* std::sample = libstdc++ selection sampling (/usr/include/c++/13/bits/stl_algo.h:5841-5905) of n out of list[0..size),
+ * order preserving; _Size is ptrdiff_t, two decisions per engine call while unsampled^2 fits the engine range. */
+static int std_sample(const int* list, int64_t size, int64_t n, romis_stream_key ek, uint32_t* ec, int* out) {
+    int no = 0; int64_t first = 0, unsampled = size;
+    if (size == 0) return 0;
+    if (n > unsampled) n = unsampled;
+    if (0xffffffffull / (uint64_t)unsampled >= (uint64_t)unsampled) {
+        while (n != 0 && unsampled >= 2) {
+            int64_t b1 = unsampled - 1;
+            int64_t x = (int64_t)lemire32(ek, ec, (uint32_t)(unsampled * b1));        /* __gen_two_uniform_ints (:3717-3725) */
+            int64_t p0 = x / b1, p1 = x % b1;
+            --unsampled;
+            if (p0 < n) { out[no++] = list[first]; --n; }
+            ++first;
+            if (n == 0) break;
+            --unsampled;
+            if (p1 < n) { out[no++] = list[first]; --n; }
+            ++first;
+        }
+    }
+    for (; n != 0; ++first) {
+        --unsampled;
+        if ((int64_t)lemire32(ek, ec, (uint32_t)(unsampled + 1)) < n) { out[no++] = list[first]; --n; }
+    }
+    return no;
+}
+
+/* areSimilar (src/rendering/neighbour_selection.cpp:7-22); lhs = the canonical pixel.  A miss pixel keeps the
+ * value-initialised geometryId 0.  The normal test compares the dot product with the ANGLE in radians (:18), as written. */
+static int are_similar(const orc_ctx* c, const romis_rmis_params* rp, const orc_hit* l, const orc_hit* r) {
+    uint32_t gl = l->mesh == (uint32_t)c->nmesh ? 0u : l->mesh, gr = r->mesh == (uint32_t)c->nmesh ? 0u : r->mesh;
+    if (rp->neighbourSameGeometry && gl != gr) return 0;
+    float depthFracDiff = fabsf(1.0f - (l->t / r->t));
+    if (depthFracDiff > rp->neighbourMaxDepthDifferenceFraction) return 0;
+    float normalsDot = dot3(l->n, r->n);
+    if (normalsDot < rp->neighbourMaxNormalAngleDifferenceRadians) return 0;
+    return 1;
+}
+
+/* indicesRandom / indicesSimilarity (neighbour_selection.cpp:24-105): out[0] = the pixel itself; returns the count */
+static int rmis_indices(const orc_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_rng* rng,
+                        int x, int y, int W, int H, int* sim, int* dis, int* out) {
+    const int k = (int)f->numNeighboursToSample, r = (int)f->spatialResampleRadius;
+    romis_stream_key ek = romis_rng_stream(rng->seed, rng->frame, ROMIS_STAGE_RMIS_NEIGH, (uint32_t)(y * W + x), ROMIS_STREAM_ENGINE);
+    uint32_t ec = 0; int no = 0;
+    int x0 = x - r < 0 ? 0 : x - r, x1 = x + r > W - 1 ? W - 1 : x + r;
+    int y0 = y - r < 0 ? 0 : y - r, y1 = y + r > H - 1 ? H - 1 : y + r;
+    out[no++] = y * W + x;                                                              /* :40 / :71 */
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_RANDOM) {                    /* :24-45 */
+        for (int i = 0; i < k; i++) {
+            /* `glm::ivec2(distrX(gen), distrY(gen))` (:42): the order of the two draws is unspecified in C++; g++, which
+             * builds the compiled reference this oracle is pinned against, evaluates the arguments right to left: y first */
+            int ny = romis_rng_uniform_int(romis_rng_bits(ek, ec++), y0, y1);
+            int nx = romis_rng_uniform_int(romis_rng_bits(ek, ec++), x0, x1);
+            out[no++] = ny * W + nx;
+        }
+        return no;
+    }
+    int ns = 0, nd = 0;
+    const orc_hit* canon = &c->gbuf[(size_t)y * W + x];
+    for (int ny = y0; ny <= y1; ny++) for (int nx = x0; nx <= x1; nx++) {               /* :59-72 */
+        if (ny == y && nx == x) continue;
+        if (are_similar(c, rp, canon, &c->gbuf[(size_t)ny * W + nx])) sim[ns++] = ny * W + nx; else dis[nd++] = ny * W + nx;
+    }
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_SIMILAR) {                   /* :79-85 */
+        if (ns < k) {
+            for (int i = 0; i < ns; i++) out[no++] = sim[i];
+            no += std_sample(dis, nd, (int64_t)k - ns, ek, &ec, out + no);
+        } else no += std_sample(sim, ns, k, ek, &ec, out + no);
+    } else {                                                                            /* EqualSimilarDissimilar :94-103 */
+        uint32_t similarsSampled = (uint32_t)k / 2u + 1u; if ((uint64_t)similarsSampled > (uint64_t)ns) similarsSampled = (uint32_t)ns;
+        uint32_t desiredDissimilars = (uint32_t)k - similarsSampled;
+        if ((uint64_t)desiredDissimilars > (uint64_t)nd) similarsSampled += (uint32_t)((uint64_t)(uint32_t)k - (uint64_t)nd - (uint64_t)similarsSampled);
+        no += std_sample(sim, ns, (int64_t)similarsSampled, ek, &ec, out + no);
+        no += std_sample(dis, nd, (int64_t)(uint32_t)((uint32_t)k - similarsSampled), ek, &ec, out + no);
+    }
+    return no;
+}
+
+int orc_render_frame_rmis(orc_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam, int W, int H,
+                          const romis_rng* rng, float* out_rgb, int32_t* neigh_xy, uint32_t* neigh_count) {
+    if (!c->tracer) { strcpy(c->err, "no scene"); return ROMIS_ERR_STATE; }
+    const int N = (int)f->numSamplesInReservoir, k = (int)f->numNeighboursToSample, r = (int)f->spatialResampleRadius;
+    if (N < 1 || N > ORC_MAX_N || W < 1 || H < 1 || k > ORC_MAX_K) { strcpy(c->err, "bad size"); return ROMIS_ERR_INVALID; }
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR) { strcpy(c->err, "Dissimilar: undefined in the reference"); return ROMIS_ERR_INVALID; }
+    if (c->W != W || c->H != H || c->N != N) {
+        size_t n = (size_t)W * H;
+        c->gbuf = (orc_hit*)realloc(c->gbuf, n * sizeof(orc_hit));
+        c->cur = (orc_sub*)realloc(c->cur, n * N * sizeof(orc_sub));
+        c->prev = (orc_sub*)realloc(c->prev, n * N * sizeof(orc_sub));
+        c->tmp = (orc_sub*)realloc(c->tmp, n * N * sizeof(orc_sub));
+        c->W = W; c->H = H; c->N = N;
+    }
+    c->have_prev = 0;
+    orc_env env; env.f = f; env.c = c; env.origin = lv(cam->origin);
+    const orc_env* e = &env;
+    const int K1 = k + 1;
+    primary_hits(c, cam, env.origin, W, H);                                             /* render.cpp:68 */
+    /* generateResampleIndicesGrid (neighbour_selection.cpp:107-122) */
+    int* idx = (int*)malloc(sizeof(int) * (size_t)W * H * K1);
+    int* cnt = (int*)malloc(sizeof(int) * (size_t)W * H);
+    const int win = (2 * r + 1) * (2 * r + 1) + 1;
+    #pragma omp parallel
+    {
+        int* sim = (int*)malloc(sizeof(int) * (size_t)win); int* dis = (int*)malloc(sizeof(int) * (size_t)win);
+        #pragma omp for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            size_t p = (size_t)y * W + x;
+            int tmp[ORC_MAX_K + 2];
+            int n = rmis_indices(c, f, rp, rng, x, y, W, H, sim, dis, tmp);
+            cnt[p] = n;
+            for (int i = 0; i < K1; i++) idx[p * K1 + i] = i < n ? tmp[i] : -1;
+        }
+        free(sim); free(dis);
+    }
+    if (neigh_count) for (size_t p = 0; p < (size_t)W * H; p++) neigh_count[p] = (uint32_t)cnt[p];
+    if (neigh_xy) for (size_t i = 0; i < (size_t)W * H * K1; i++) {
+        neigh_xy[2 * i] = idx[i] < 0 ? -1 : idx[i] % W; neigh_xy[2 * i + 1] = idx[i] < 0 ? -1 : idx[i] / W;
+    }
+    v3* acc = (v3*)calloc((size_t)W * H, sizeof(v3));
+    for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                            /* render.cpp:72 */
+        #pragma omp parallel for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* genInitialSamples :74 */
+            size_t p = (size_t)y * W + x;
+            gen_canonical(e, rng, ROMIS_STAGE_RMIS_INITIAL0 + it, (uint32_t)p, gen_ray_dir(cam, x, y, W, H), &c->gbuf[p], &c->cur[p * N]);
+        }
+        #pragma omp parallel for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* :79-112 */
+            size_t p = (size_t)y * W + x;
+            const orc_hit* h = &c->gbuf[p]; v3 dir = gen_ray_dir(cam, x, y, W, H);
+            const int n = cnt[p];
+            v3 finalColor = V3(0, 0, 0);
+            for (int a = 0; a < n; a++) {
+                const orc_sub* px = &c->cur[(size_t)idx[p * K1 + a] * N];
+                for (int j = 0; j < N; j++) {
+                    float misWeight;
+                    if (rp->misWeightRMIS == ROMIS_MIS_EQUAL) misWeight = 1.0f / (float)n;                         /* :97 */
+                    else {                                                              /* generalisedBalanceHeuristic, render_utils.cpp:179-187 */
+                        float numerator = target_pdf(e, px[j].pos, px[j].col, dir, h);
+                        float denominator = FLT_MIN;
+                        for (int b = 0; b < n; b++) {
+                            int q = idx[p * K1 + b];
+                            denominator += target_pdf(e, px[j].pos, px[j].col, gen_ray_dir(cam, q % W, q / W, W, H), &c->gbuf[q]);
+                        }
+                        misWeight = numerator / denominator;
+                    }
+                    v3 sampleColor = visible(e, px[j].pos, dir, h) ? compute_shading(e, px[j].pos, px[j].col, dir, h) : V3(0, 0, 0);   /* :103-105 */
+                    finalColor = add3(finalColor, div3(scale3(scale3(sampleColor, misWeight), px[j].W), (float)N));                  /* :106 */
+                }
+            }
+            acc[p] = add3(acc[p], finalColor);                                          /* :111 */
+        }
+    }
+    if (out_rgb) {                                                                      /* combineToScreen, render_utils.cpp:68-85 */
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            v3 color = div3(acc[(size_t)y * W + x], (float)rp->maxIterationsMIS);
+            if (f->enableToneMapping) {
+                v3 mapped = V3(1.0f - romis_expf(f->exposure * -color.x), 1.0f - romis_expf(f->exposure * -color.y), 1.0f - romis_expf(f->exposure * -color.z));
+                float ig = 1.0f / f->gamma;
+                color = V3(romis_powf(mapped.x, ig), romis_powf(mapped.y, ig), romis_powf(mapped.z, ig));
+            }
+            size_t i = (size_t)(H - 1 - y) * W + x;
+            out_rgb[3 * i] = color.x; out_rgb[3 * i + 1] = color.y; out_rgb[3 * i + 2] = color.z;
+        }
+    }
+    free(idx); free(cnt); free(acc);
     return 0;
 }
 

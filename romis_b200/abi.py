@@ -48,6 +48,16 @@ class romis_features(C.Structure):
         "temporalClampM", "enableToneMapping")] + [("gamma", C.c_float), ("exposure", C.c_float)]
 
 
+class romis_rmis_params(C.Structure):
+    _fields_ = [("maxIterationsMIS", C.c_uint32), ("misWeightRMIS", C.c_uint32), ("neighbourSelectionStrategy", C.c_uint32),
+                ("neighbourSameGeometry", C.c_uint32), ("neighbourMaxDepthDifferenceFraction", C.c_float),
+                ("neighbourMaxNormalAngleDifferenceRadians", C.c_float)]
+
+
+ROMIS_MIS_EQUAL, ROMIS_MIS_BALANCE = 0, 1
+ROMIS_NEIGHBOURS_RANDOM, ROMIS_NEIGHBOURS_SIMILAR, ROMIS_NEIGHBOURS_DISSIMILAR, ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR = 0, 1, 2, 3
+
+
 class romis_camera(C.Structure):
     _fields_ = [("origin", f3), ("quat", f4), ("half_width", C.c_float), ("half_height", C.c_float)]
 

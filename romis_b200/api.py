@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import abi
-from .scene import Camera, Features, Scene, LIGHT_DTYPE
+from .scene import Camera, Features, RmisParams, Scene, LIGHT_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libromis_gpu.so")
@@ -25,6 +25,7 @@ EXPORTS = [
     "romis_set_capture", "romis_download_reservoirs", "romis_download_gbuffer", "romis_trace_rays",
     "romis_set_stage_timing", "romis_last_frame_timings", "romis_host_alloc", "romis_host_free",
     "romis_row_hit_counts", "romis_band_prepare", "romis_peer_export", "romis_peer_attach", "romis_peer_detach", "romis_peer_error",
+    "romis_render_frame_rmis", "romis_download_rmis_neighbours",
 ]
 PEER_BLOB_BYTES = 512
 
@@ -54,6 +55,9 @@ def load_library() -> C.CDLL:
     L.romis_render_frame.argtypes = frame_args + [vp]
     L.romis_render_frame_device.argtypes = frame_args + [C.POINTER(vp)]
     L.romis_frame_begin.argtypes = frame_args
+    L.romis_render_frame_rmis.argtypes = [vp, C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params), C.POINTER(abi.romis_camera),
+                                          ci, ci, C.POINTER(abi.romis_rng), vp]
+    L.romis_download_rmis_neighbours.argtypes = [vp, vp, vp]
     L.romis_frame_spatial_pass.argtypes = [vp, ci]
     L.romis_frame_end.argtypes = [vp, vp]
     L.romis_reset_history.argtypes = [vp]; L.romis_synchronize.argtypes = [vp]
@@ -193,6 +197,24 @@ class RestirRenderer:
         self._check(self.lib.romis_render_frame_device(self.ctx, C.byref(f), C.byref(cam), W, H, int(history_valid), C.byref(r), C.byref(dev)))
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         return dev.value
+
+    def render_frame_rmis(self, features: Features, rmis: RmisParams, camera, W: int, H: int, seed: int, frame: int,
+                          want_image: bool = True):
+        """renderRMIS (reference src/rendering/render.cpp:64-119): the R-MIS estimator, no temporal state.  Returns the
+        float RGB image [H, W, 3] in Screen::pixels() layout, or None with want_image=False (image stays on the device)."""
+        f = features.to_abi(); rp = rmis.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
+        out = np.zeros((H, W, 3), np.float32) if want_image else None
+        self._check(self.lib.romis_render_frame_rmis(self.ctx, C.byref(f), C.byref(rp), C.byref(cam), W, H, C.byref(r),
+                                                     out.ctypes.data if want_image else None))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        self._rmis_k1 = features.numNeighboursToSample + 1
+        return out
+
+    def rmis_neighbours(self):
+        """Neighbour grid of the last R-MIS frame: (xy [H, W, k+1, 2] with -1 for unused entries, count [H, W])."""
+        xy = np.full((self.H, self.W, self._rmis_k1, 2), -1, np.int32); cnt = np.zeros((self.H, self.W), np.uint32)
+        self._check(self.lib.romis_download_rmis_neighbours(self.ctx, xy.ctypes.data, cnt.ctypes.data))
+        return xy, cnt
 
     def reset_history(self):
         self._check(self.lib.romis_reset_history(self.ctx))

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libromis_gpu.so")
-SOURCES = ["romis_gpu.cu", "k_initial.cu", "k_temporal.cu", "k_spatial.cu", "k_misc.cu", "bvh.cpp"]
+SOURCES = ["romis_gpu.cu", "k_initial.cu", "k_temporal.cu", "k_spatial.cu", "k_rmis.cu", "k_misc.cu", "bvh.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", "g++",

@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         res_store(out, y - fr.ey0, x, r, N);
         return;
     }
-    romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_ENGINE);
-    romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_INITIAL, pixel, ROMIS_STREAM_RAND);
+    romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, fr.initial_stage, pixel, ROMIS_STREAM_ENGINE);
+    romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, fr.initial_stage, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
     ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;               // light.cpp:58-60
     const float invPdf = 1.0f / (float)sc.n_lights;                                 // light.cpp:80

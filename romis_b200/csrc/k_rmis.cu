@@ -1,0 +1,205 @@
+// k_rmis.cu -- R-MIS mode (renderRMIS, reference src/rendering/render.cpp:64-119): the neighbour index grid
+// (generateResampleIndicesGrid, src/rendering/neighbour_selection.cpp:107-122), the per-iteration gather over the k+1
+// neighbourhood pixels with equal or balance-heuristic MIS weights (render.cpp:79-112; generalisedBalanceHeuristic,
+// render_utils.cpp:179-187) and combineToScreen (render_utils.cpp:68-85).  The initial RIS of every iteration is
+// initial_kernel (k_initial.cu) under the iteration's own random-stream stage.
+#include "reservoir.cuh"
+#include "launch.hpp"
+
+namespace romis {
+
+// libstdc++ 13 uniform_int_distribution on a 32-bit engine: Lemire's method WITH its rejection step
+// (bits/uniform_int_dist.h:255-281), as std::sample instantiates it inside the reference.  Value in [0, range).
+__device__ __forceinline__ uint32_t lemire32(romis_stream_key ek, uint32_t& ec, uint32_t range) {
+    uint64_t product = (uint64_t)romis_rng_bits(ek, ec++) * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+        const uint32_t threshold = (0u - range) % range;
+        while (low < threshold) { product = (uint64_t)romis_rng_bits(ek, ec++) * (uint64_t)range; low = (uint32_t)product; }
+    }
+    return (uint32_t)(product >> 32);
+}
+
+// areSimilar (neighbour_selection.cpp:7-22); `own` is the canonical pixel (lhs).  A miss pixel keeps the value-initialised
+// geometryId 0.  The normal test compares the dot product with the ANGLE in radians (:18), as the reference does.
+__device__ __forceinline__ bool are_similar(const romis_rmis_params& rp, uint32_t n_meshes, float4 own, uint32_t own_mesh, float4 nb, uint32_t nb_mesh) {
+    if (rp.neighbourSameGeometry) {
+        uint32_t gl = own_mesh == n_meshes ? 0u : own_mesh, gr = nb_mesh == n_meshes ? 0u : nb_mesh;
+        if (gl != gr) return false;
+    }
+    float depthFracDiff = fabsf(1.0f - (own.x / nb.x));
+    if (depthFracDiff > rp.neighbourMaxDepthDifferenceFraction) return false;
+    float normalsDot = dot3(V3(own.y, own.z, own.w), V3(nb.y, nb.z, nb.w));
+    if (normalsDot < rp.neighbourMaxNormalAngleDifferenceRadians) return false;
+    return true;
+}
+
+// The window of one pixel, classified: bit i of `mask` (scan order, rows of the clipped window) = "similar".
+struct RmisWindow { int x0, x1, y0, y1, x, y; uint32_t mask[ROMIS_RMIS_WORDS]; };
+
+// std::sample (libstdc++ selection sampling, bits/stl_algo.h:5841-5905) of n out of the `size` window pixels of class
+// `cls`, in scan order, without materialising the list: one decision per element, two decisions per engine call while
+// unsampled^2 fits the 32-bit engine range (__gen_two_uniform_ints).  all = true copies the class without draws
+// (neighbour_selection.cpp:80).  Appends packed (y << 16 | x) entries at plane `no` of the pixel's neighbour column.
+__device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32_t size, uint32_t n, bool all,
+                                           romis_stream_key ek, uint32_t& ec, uint32_t* __restrict__ col, size_t plane, int& no) {
+    if (size == 0u) return;
+    if (n > size) n = size;
+    if (all) n = size;
+    if (n == 0u) return;
+    uint32_t unsampled = size;
+    const bool two_mode = 0xffffffffu / unsampled >= unsampled;
+    bool in_pairs = two_mode, have_p1 = false; uint32_t p1 = 0u;
+    int i = 0;
+    for (int ny = w.y0; ny <= w.y1 && n != 0u; ny++) {
+        for (int nx = w.x0; nx <= w.x1; nx++, i++) {
+            if (ny == w.y && nx == w.x) continue;
+            if ((((w.mask[i >> 5] >> (i & 31)) & 1u) != 0u) != cls) continue;
+            bool take;
+            if (all) take = true;
+            else if (have_p1) { have_p1 = false; --unsampled; take = p1 < n; }
+            else {
+                if (in_pairs && unsampled < 2u) in_pairs = false;       // the pair loop's `unsampled >= 2` (:5870)
+                if (in_pairs) {
+                    const uint32_t b1 = unsampled - 1u;
+                    const uint32_t xx = lemire32(ek, ec, unsampled * b1);
+                    const uint32_t p0 = xx / b1; p1 = xx % b1; have_p1 = true;
+                    --unsampled; take = p0 < n;
+                } else { --unsampled; take = lemire32(ek, ec, unsampled + 1u) < n; }
+            }
+            if (take) { col[(size_t)no * plane] = ((uint32_t)ny << 16) | (uint32_t)nx; no++; --n; if (n == 0u) break; }
+        }
+    }
+}
+
+// generateResampleIndicesGrid: indicesRandom (neighbour_selection.cpp:24-45) / indicesSimilarity (:47-105)
+__global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, FrameDev fr, GBufDev g, RmisDev rm) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.H) return;
+    const int k = (int)fr.f.numNeighboursToSample, r = (int)fr.f.spatialResampleRadius;
+    const size_t p = (size_t)y * fr.W + x;
+    uint32_t* col = rm.nb + p;
+    romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_RMIS_NEIGH, (uint32_t)p, ROMIS_STREAM_ENGINE);
+    uint32_t ec = 0;
+    int no = 0;
+    RmisWindow w;
+    w.x = x; w.y = y;
+    w.x0 = max(0, x - r); w.x1 = min(fr.W - 1, x + r);
+    w.y0 = max(0, y - r); w.y1 = min(fr.H - 1, y + r);
+    col[0] = ((uint32_t)y << 16) | (uint32_t)x; no = 1;                            // :40 / :71 the pixel itself, always
+    if (rm.p.neighbourSelectionStrategy == ROMIS_NEIGHBOURS_RANDOM) {
+        for (int i = 0; i < k; i++) {
+            // `glm::ivec2(distrX(gen), distrY(gen))` (:42): the order of the two draws is unspecified in C++; g++, which
+            // builds the compiled reference the oracle is pinned against, evaluates them right to left: y first
+            int ny = romis_rng_uniform_int(romis_rng_bits(ek, ec++), w.y0, w.y1);
+            int nx = romis_rng_uniform_int(romis_rng_bits(ek, ec++), w.x0, w.x1);
+            col[(size_t)no * rm.plane] = ((uint32_t)ny << 16) | (uint32_t)nx; no++;
+        }
+    } else {
+        // classify the window (:59-72)
+        const float4 own = g.tn[p]; const uint32_t own_mesh = g.mesh[p];
+        uint32_t ns = 0, nd = 0, word = 0; int i = 0;
+        for (int ny = w.y0; ny <= w.y1; ny++) {
+            const size_t row = (size_t)ny * fr.W;
+            for (int nx = w.x0; nx <= w.x1; nx++, i++) {
+                if (!(ny == y && nx == x)) {
+                    const bool s = are_similar(rm.p, (uint32_t)sc.n_meshes, own, own_mesh, g.tn[row + nx], g.mesh[row + nx]);
+                    if (s) { ns++; word |= 1u << (i & 31); } else nd++;
+                }
+                if ((i & 31) == 31) { w.mask[i >> 5] = word; word = 0; }
+            }
+        }
+        if (i & 31) w.mask[i >> 5] = word;
+        const uint32_t ku = (uint32_t)k;
+        if (rm.p.neighbourSelectionStrategy == ROMIS_NEIGHBOURS_SIMILAR) {          // :79-85
+            if (ns < ku) {
+                emit_class(w, true, ns, ns, true, ek, ec, col, rm.plane, no);
+                emit_class(w, false, nd, ku - ns, false, ek, ec, col, rm.plane, no);
+            } else emit_class(w, true, ns, ku, false, ek, ec, col, rm.plane, no);
+        } else {                                                                    // EqualSimilarDissimilar :94-103
+            uint32_t similarsSampled = min(ku / 2u + 1u, ns);
+            const uint32_t desiredDissimilars = ku - similarsSampled;
+            if (desiredDissimilars > nd) similarsSampled += ku - nd - similarsSampled;
+            emit_class(w, true, ns, similarsSampled, false, ek, ec, col, rm.plane, no);
+            emit_class(w, false, nd, ku - similarsSampled, false, ek, ec, col, rm.plane, no);
+        }
+    }
+    for (; no < rm.K1; no++) col[(size_t)no * rm.plane] = 0xffffffffu;
+}
+
+// One iteration's gather (render.cpp:79-112): every pixel shades the samples of its neighbourhood pixels at ITS OWN hit
+// point, each weighted by the MIS weight and the sample's outputWeight, with a shadow ray per sample.
+template <int NT>
+__global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.H) return;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const bool es = fr.f.enableShading != 0;
+    const size_t p = (size_t)y * fr.W + x;
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    // A miss pixel shades every sample to exactly +0 (see target_pdf) and the balance weight is 0 / (FLT_MIN + ...) = 0:
+    // the iteration adds +0 to the accumulator, which leaves it unchanged.
+    if (c.miss) return;
+    uint32_t q[ROMIS_MAX_K + 1]; int n = 0;
+    for (int a = 0; a < rm.K1; a++) { uint32_t e = rm.nb[(size_t)a * rm.plane + p]; if (e != 0xffffffffu) q[n++] = e; }
+    const bool balance = rm.p.misWeightRMIS == ROMIS_MIS_BALANCE;
+    const float equalWeight = 1.0f / (float)n;                                      // render.cpp:97 (size_t -> float)
+    v3 finalColor = V3(0, 0, 0);
+    for (int a = 0; a < n; a++) {
+        const int qy = (int)(q[a] >> 16), qx = (int)(q[a] & 0xffffu);
+        for (int j = 0; j < N; j++) {
+            const uint4 rec = res_rec(in, qy, j)[qx];
+            const float Wj = __uint_as_float(rec.w);
+            // W == 0 contributes (+-0) whatever the weight and the visibility: the sum keeps its bits
+            if (Wj == 0.0f) continue;
+            v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
+            const v3 shading = compute_shading(c, es, pos, col);
+            if (shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) continue;      // same: adds (+-0)
+            float misWeight = equalWeight;
+            if (balance) {                                                          // render_utils.cpp:179-187
+                const float numerator = length3(shading);                           // targetPDF at this pixel
+                float denominator = FLT_MIN;
+                for (int b = 0; b < n; b++) {
+                    const int by = (int)(q[b] >> 16), bx = (int)(q[b] & 0xffffu);
+                    PixCtx cb = make_ctx(sc, fr, g, bx, by);
+                    denominator += target_pdf(cb, es, pos, col);
+                }
+                misWeight = numerator / denominator;
+            }
+            v3 sampleColor = visible(sc, c, pos) ? shading : V3(0, 0, 0);           // render.cpp:103-105
+            finalColor = add3(finalColor, div3(scale3(scale3(sampleColor, misWeight), Wj), (float)N));      // :106
+        }
+    }
+    float4 acc = rm.acc[p];
+    rm.acc[p] = make_float4(acc.x + finalColor.x, acc.y + finalColor.y, acc.z + finalColor.z, 0.0f);        // :111
+}
+
+// combineToScreen (render_utils.cpp:68-85): average over the iterations, tone map, Screen layout
+__global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.H) return;
+    const float4 acc = rm.acc[(size_t)y * fr.W + x];
+    v3 color = div3(V3(acc.x, acc.y, acc.z), (float)rm.p.maxIterationsMIS);
+    if (fr.f.enableToneMapping) {
+        float ig = 1.0f / fr.f.gamma;
+        color = V3(romis_powf(1.0f - romis_expf(fr.f.exposure * -color.x), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.y), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.z), ig));
+    }
+    size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;
+    rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
+}
+
+void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm) {
+    rmis_neighbours_kernel<<<grid, block, 0, s>>>(sc, fr, g, rm);
+}
+void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm) {
+    ROMIS_DISPATCH_N(N, (rmis_gather_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rm)));
+}
+void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
+    rmis_combine_kernel<<<grid, block, 0, s>>>(fr, rm, rgb);
+}
+}  // namespace romis

@@ -77,6 +77,10 @@ struct romis_ctx {
     uint32_t pass_token = 0, frame_token = 0;
     bool exported = false;
 
+    // R-MIS (romis_render_frame_rmis): neighbour grid and accumulator of the last frame
+    DevBuf rmis_nb, rmis_acc;
+    int rmis_W = 0, rmis_H = 0, rmis_K1 = 0;
+
     // parity capture
     bool capture = false;
     std::map<int, DevBuf> captured;
@@ -164,7 +168,7 @@ extern "C" void romis_destroy(romis_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
-                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2]}) b->release();
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc}) b->release();
     romis_peer_detach(c);
     c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
@@ -426,6 +430,7 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
     fr.f = *f; fr.seed = rng->seed; fr.frame = rng->frame;
     fr.W = W; fr.H = H; fr.y0 = c->y0; fr.y1 = c->y1; fr.ey0 = c->ey0; fr.ey1 = c->ey1;
+    fr.initial_stage = ROMIS_STAGE_INITIAL;
     // halo rows are only meaningful up to this frame's radius
     const int r_now = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
     const int pey0 = std::max(0, c->y0 - r_now), pey1 = std::min(H, c->y1 + r_now);
@@ -713,6 +718,89 @@ extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, 
     int rc = render_common(c, f, cam, W, H, history_valid, rng, nullptr);
     if (rc == ROMIS_OK && dev_rgb) *dev_rgb = (const float*)c->rgb.p;
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// R-MIS frame (renderRMIS, reference src/rendering/render.cpp:64-119)
+// ------------------------------------------------------------------------------------------------
+extern "C" int romis_render_frame_rmis(romis_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                                       int W, int H, const romis_rng* rng, float* out_rgb) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_render_frame_rmis: frame in flight");
+    if (!rp) return fail(c, ROMIS_ERR_INVALID, "null rmis parameters");
+    int rc = validate(c, f, cam, W, H, rng);
+    if (rc) return rc;
+    if (c->band_y1 > c->band_y0) return fail(c, ROMIS_ERR_INVALID, "romis_render_frame_rmis: row bands are not supported in R-MIS mode");
+    if (rp->maxIterationsMIS < 1) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS must be >= 1");
+    if (rp->misWeightRMIS > ROMIS_MIS_BALANCE) return fail(c, ROMIS_ERR_INVALID, "unhandled MIS weight type (render.cpp:99)");
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR)
+        return fail(c, ROMIS_ERR_INVALID, "NeighbourSelectionStrategy::Dissimilar is undefined behaviour in the reference (neighbour_selection.cpp:88-93)");
+    if (rp->neighbourSelectionStrategy > ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR) return fail(c, ROMIS_ERR_INVALID, "unknown neighbour selection strategy");
+    if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM && f->spatialResampleRadius > ROMIS_RMIS_MAX_R)
+        return fail(c, ROMIS_ERR_INVALID, "spatialResampleRadius must be <= 30 for similarity-based neighbour selection (ui.cpp:308)");
+    if (rp->maxIterationsMIS > 0x7fffffffu - ROMIS_STAGE_RMIS_INITIAL0) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS too large");
+    RCHECK(c, cudaSetDevice(c->device));
+    if ((rc = ensure_frame_buffers(c, f, W, H))) return rc;
+
+    const int K1 = (int)f->numNeighboursToSample + 1;
+    const size_t px = (size_t)W * H;
+    RCHECK(c, c->rmis_nb.ensure(px * K1 * sizeof(uint32_t)));
+    RCHECK(c, c->rmis_acc.ensure(px * sizeof(float4)));
+    c->rmis_W = W; c->rmis_H = H; c->rmis_K1 = K1;
+    RmisDev rm; rm.p = *rp; rm.nb = (uint32_t*)c->rmis_nb.p; rm.acc = (float4*)c->rmis_acc.p; rm.K1 = K1; rm.plane = px;
+
+    FrameDev& fr = c->fr;
+    fr.cam.origin.x = cam->origin[0]; fr.cam.origin.y = cam->origin[1]; fr.cam.origin.z = cam->origin[2];
+    fr.cam.qw = cam->quat[0]; fr.cam.qx = cam->quat[1]; fr.cam.qy = cam->quat[2]; fr.cam.qz = cam->quat[3];
+    fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
+    fr.f = *f; fr.seed = rng->seed; fr.frame = rng->frame;
+    fr.W = W; fr.H = H; fr.y0 = 0; fr.y1 = H; fr.ey0 = 0; fr.ey1 = H;
+
+    c->marks.clear(); c->n_launches = 0; c->timings_pending = true;
+    std::memset(&c->last, 0, sizeof c->last);
+    RCHECK(c, cudaEventRecord(c->ev_begin, c->stream));
+    const dim3 grid = grid_for(W, H);
+    const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
+    RCHECK(c, cudaMemsetAsync(c->rmis_acc.p, 0, px * sizeof(float4), c->stream));
+    launch_primary(c->stream, grid, kBlock, c->sc, fr, gbuf(c), 0, H);                      // render.cpp:68
+    launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, gbuf(c), rm);                // :69
+    c->n_launches += 2;
+    RCHECK(c, cudaGetLastError());
+    for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72
+        fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
+        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work)); // :74
+        launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        c->n_launches += 2;
+        RCHECK(c, cudaGetLastError());
+    }
+    fr.initial_stage = ROMIS_STAGE_INITIAL;
+    launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);                 // :118
+    c->n_launches++;
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
+    if (out_rgb) RCHECK(c, cudaMemcpyAsync(out_rgb, c->rgb.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    return ROMIS_OK;
+}
+
+extern "C" int romis_download_rmis_neighbours(romis_ctx* c, int32_t* xy, uint32_t* count) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->rmis_K1 || !c->rmis_nb.p) return fail(c, ROMIS_ERR_STATE, "romis_download_rmis_neighbours: no R-MIS frame rendered");
+    RCHECK(c, cudaSetDevice(c->device));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    const size_t px = (size_t)c->rmis_W * c->rmis_H; const int K1 = c->rmis_K1;
+    std::vector<uint32_t> nb(px * K1);
+    RCHECK(c, cudaMemcpy(nb.data(), c->rmis_nb.p, nb.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < px; p++) {
+        uint32_t n = 0;
+        for (int a = 0; a < K1; a++) {
+            const uint32_t e = nb[(size_t)a * px + p];
+            if (e != 0xffffffffu) n++;
+            if (xy) { xy[(p * K1 + a) * 2] = e == 0xffffffffu ? -1 : (int32_t)(e & 0xffffu); xy[(p * K1 + a) * 2 + 1] = e == 0xffffffffu ? -1 : (int32_t)(e >> 16); }
+        }
+        if (count) count[p] = n;
+    }
+    return ROMIS_OK;
 }
 
 extern "C" int romis_halo_region(romis_ctx* c, int which, void** dev_ptr, size_t* bytes) {

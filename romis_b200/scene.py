@@ -56,6 +56,22 @@ class Features:
 
 
 @dataclass
+class RmisParams:
+    """The fields of `Features` only the R-MIS mode reads, with the reference's defaults (common.h:110-121)."""
+    maxIterationsMIS: int = 5
+    misWeightRMIS: int = abi.ROMIS_MIS_EQUAL
+    neighbourSelectionStrategy: int = abi.ROMIS_NEIGHBOURS_SIMILAR
+    neighbourSameGeometry: bool = True
+    neighbourMaxDepthDifferenceFraction: float = 0.10
+    neighbourMaxNormalAngleDifferenceRadians: float = 0.436332
+
+    def to_abi(self) -> abi.romis_rmis_params:
+        return abi.romis_rmis_params(int(self.maxIterationsMIS), int(self.misWeightRMIS), int(self.neighbourSelectionStrategy),
+                                     int(self.neighbourSameGeometry), float(self.neighbourMaxDepthDifferenceFraction),
+                                     float(self.neighbourMaxNormalAngleDifferenceRadians))
+
+
+@dataclass
 class Camera:
     """`CameraConfig` of the reference (src/utils/config.h:21-26); defaults = the nightclub view."""
     fov_deg: float = 30.0

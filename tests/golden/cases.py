@@ -1,5 +1,6 @@
 """Golden cases shared by the generator (gen_golden.py, needs /root/reference) and the tests."""
-from romis_b200.scene import Camera, Features
+from romis_b200 import abi
+from romis_b200.scene import Camera, Features, RmisParams
 
 NIGHTCLUB_CAM = Camera()                                            # reference src/utils/config.h:21-26
 CORNELL_CAM = Camera(50.0, 3.0, (0.0, 0.0, 0.0), (20.0, 20.0, 0.0))   # TOML fallback camera, src/utils/config.cpp:249-252
@@ -23,3 +24,22 @@ CASES = {
     "nightclub_no_temporal": ("CornellNightClub", 32, 24, Features(temporalReuse=False, spatialResampleRadius=30, numNeighboursToSample=10), NIGHTCLUB_CAM, 2, 53),
 }
 SCENES = ["SingleTriangle", "Cube", "CubeTextured", "CornellBox", "CornellBoxParallelogramLight", "CornellNightClub", "Monkey"]
+
+# R-MIS mode (renderRMIS, reference src/rendering/render.cpp:64-119): name -> (scene, W, H, Features, RmisParams, Camera, seed, frame)
+RMIS_CASES = {
+    "rmis_nightclub_similar_equal": ("CornellNightClub", 40, 30, Features(), RmisParams(maxIterationsMIS=3), NIGHTCLUB_CAM, 61, 0),
+    "rmis_nightclub_similar_balance": ("CornellNightClub", 36, 28, Features(numSamplesInReservoir=1),
+                                       RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE), NIGHTCLUB_CAM, 67, 3),
+    "rmis_nightclub_random_balance": ("CornellNightClub", 32, 24, Features(numNeighboursToSample=3, spatialResampleRadius=30),
+                                      RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE,
+                                                 neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_RANDOM), NIGHTCLUB_CAM, 71, 1),
+    "rmis_monkey_esd_balance": ("Monkey", 40, 33, Features(numNeighboursToSample=10, spatialResampleRadius=4, numSamplesInReservoir=3),
+                                RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE, neighbourSameGeometry=False,
+                                           neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR), CORNELL_CAM, 73, 0),
+    # window smaller than k: std::sample returns fewer than k neighbours
+    "rmis_cube_small_window": ("CubeTextured", 24, 24, Features(numNeighboursToSample=10, spatialResampleRadius=1, initialSamplesVisibilityCheck=True,
+                                                                 gamma=2.2, exposure=0.8),
+                               RmisParams(maxIterationsMIS=1, neighbourMaxDepthDifferenceFraction=0.02), CORNELL_CAM, 79, 2),
+    "rmis_cornell_esd_equal_r30": ("CornellBoxParallelogramLight", 40, 40, Features(spatialResampleRadius=30, numSamplesInReservoir=5, initialLightSamples=8),
+                                   RmisParams(maxIterationsMIS=2, neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR), CORNELL_CAM, 83, 0),
+}

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from oracle.pyoracle import RefLib, REF_FLAG_SPLIT_SPATIAL, build_ref  # noqa: E402
 from romis_b200 import abi  # noqa: E402
-from cases import CASES, SCENES  # noqa: E402
+from cases import CASES, RMIS_CASES, SCENES  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -37,7 +37,8 @@ def main():
     for s in SCENES:
         ref.load_prebuilt(s)
         ref.export_scene(s).save(os.path.join(OUT, "scenes", s + ".npz"))
-    for name, (scene, W, H, feat, cam, frames, seed) in CASES.items():
+    only_rmis = "--rmis-only" in sys.argv     # the ReSTIR vectors are left as committed
+    for name, (scene, W, H, feat, cam, frames, seed) in ({} if only_rmis else CASES).items():
         ref.load_prebuilt(scene)
         d = {"camera": cam_array(ref.make_camera(cam, W, H))}
         for fr in range(frames):
@@ -54,6 +55,12 @@ def main():
                 for fld in ("position", "color", "W", "M", "wSum"):
                     d[f"{p}s{pid}_{fld}"] = getattr(st, fld)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "ok")
+    for name, (scene, W, H, feat, rmis, cam, seed, frame) in RMIS_CASES.items():
+        ref.load_prebuilt(scene)
+        img, xy, cnt = ref.render_frame_rmis(feat, rmis, cam, W, H, seed, frame)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), camera=cam_array(ref.make_camera(cam, W, H)), image=img,
+                            neighbours=xy.astype(np.int16), count=cnt.astype(np.uint8))
         print(name, "ok")
 
 

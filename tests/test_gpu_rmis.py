@@ -1,0 +1,91 @@
+"""R-MIS mode on the GPU (romis_render_frame_rmis, through the C-ABI) against the oracle and the golden vectors the
+REFERENCE's renderRMIS produced (reference src/rendering/render.cpp:64-119).  Neighbour grid and counts bit-exact
+(integer work); image within 1e-4 relative / 1e-3 RMSE (north_star) and, as built, bit-exact."""
+import numpy as np
+import pytest
+
+from romis_b200 import abi
+from romis_b200.scene import Features, RmisParams, synthetic_lights
+from cases import NIGHTCLUB_CAM, RMIS_CASES
+from common import assert_bits_equal, assert_rel_close, camera_from_array, load_golden, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def renderer():
+    from romis_b200.api import RestirRenderer
+    r = RestirRenderer(0)
+    yield r
+    r.close()
+
+
+@pytest.mark.parametrize("case", sorted(RMIS_CASES))
+def test_rmis_gpu_matches_oracle_and_golden(case, renderer, oracle_factory):
+    scene_name, W, H, feat, rmis, _cam, seed, frame = RMIS_CASES[case]
+    g = load_golden(case)
+    scene = load_scene(scene_name)
+    cam = camera_from_array(g["camera"])
+    orc = oracle_factory(); orc.upload_scene(scene)
+    oimg, oxy, ocnt = orc.render_frame_rmis(feat, rmis, cam, W, H, seed, frame)
+    renderer.upload_scene(scene)
+    gimg = renderer.render_frame_rmis(feat, rmis, cam, W, H, seed, frame)
+    gxy, gcnt = renderer.rmis_neighbours()
+    assert_bits_equal(gcnt, ocnt, f"{case} neighbour count vs oracle")
+    assert_bits_equal(gxy, oxy, f"{case} neighbour grid vs oracle")
+    assert_bits_equal(gcnt, g["count"].astype(np.uint32), f"{case} neighbour count vs reference")
+    assert_bits_equal(gxy, g["neighbours"].astype(np.int32), f"{case} neighbour grid vs reference")
+    assert_rel_close(gimg, oimg, 1e-4, f"{case} image vs oracle")
+    rmse = float(np.sqrt(np.mean((gimg.astype(np.float64) - g["image"]) ** 2)))
+    assert rmse <= 1e-3, f"{case} image RMSE vs reference {rmse}"
+    assert_bits_equal(gimg, g["image"], f"{case} image vs reference")
+
+
+def test_rmis_larger_frame_many_lights(renderer, oracle_factory):
+    """256x144 nightclub geometry with 4096 synthetic lights, balance heuristic, every strategy: GPU = oracle bit for bit."""
+    scene = load_scene("CornellNightClub"); scene.lights = synthetic_lights(4096, seed=5)
+    W, H = 256, 144
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    orc = oracle_factory(); orc.upload_scene(scene); renderer.upload_scene(scene)
+    feat = Features(initialSamplesVisibilityCheck=True)
+    for strategy in (abi.ROMIS_NEIGHBOURS_RANDOM, abi.ROMIS_NEIGHBOURS_SIMILAR, abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR):
+        rp = RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE, neighbourSelectionStrategy=strategy)
+        oimg, oxy, ocnt = orc.render_frame_rmis(feat, rp, cam, W, H, 99, 4)
+        gimg = renderer.render_frame_rmis(feat, rp, cam, W, H, 99, 4)
+        gxy, gcnt = renderer.rmis_neighbours()
+        assert_bits_equal(gcnt, ocnt, f"strategy {strategy} count"); assert_bits_equal(gxy, oxy, f"strategy {strategy} grid")
+        assert_bits_equal(gimg, oimg, f"strategy {strategy} image")
+
+
+def test_rmis_leaves_restir_history_alone(renderer, oracle_factory):
+    """An R-MIS frame between two ReSTIR frames must not disturb the temporal history (it works in a scratch buffer)."""
+    scene = load_scene("CornellNightClub"); W, H = 48, 32
+    cam = NIGHTCLUB_CAM.to_abi(W, H); feat = Features()
+    renderer.upload_scene(scene); renderer.reset_history()
+    renderer.render_frame(feat, cam, W, H, False, 5, 0)
+    a = renderer.render_frame(feat, cam, W, H, True, 5, 1)
+    renderer.reset_history()
+    renderer.render_frame(feat, cam, W, H, False, 5, 0)
+    renderer.render_frame_rmis(feat, RmisParams(maxIterationsMIS=1), cam, W, H, 5, 7)
+    b = renderer.render_frame(feat, cam, W, H, True, 5, 1)
+    assert_bits_equal(a, b, "ReSTIR frame 1 with and without an R-MIS frame in between")
+
+
+def test_rmis_error_paths(renderer):
+    from romis_b200.api import RomisError
+    scene = load_scene("Cube"); renderer.upload_scene(scene)
+    cam = NIGHTCLUB_CAM.to_abi(16, 16)
+    with pytest.raises(RomisError):
+        renderer.render_frame_rmis(Features(), RmisParams(neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_DISSIMILAR), cam, 16, 16, 1, 0)
+    with pytest.raises(RomisError):
+        renderer.render_frame_rmis(Features(), RmisParams(maxIterationsMIS=0), cam, 16, 16, 1, 0)
+    with pytest.raises(RomisError):
+        renderer.render_frame_rmis(Features(), RmisParams(misWeightRMIS=7), cam, 16, 16, 1, 0)
+    with pytest.raises(RomisError):
+        renderer.render_frame_rmis(Features(spatialResampleRadius=31), RmisParams(), cam, 16, 16, 1, 0)
+    renderer.set_band(0, 8)
+    try:
+        with pytest.raises(RomisError):
+            renderer.render_frame_rmis(Features(), RmisParams(), cam, 16, 16, 1, 0)
+    finally:
+        renderer.set_band(0, 0)

@@ -163,6 +163,11 @@ int romis_render_frame_device(romis_ctx* ctx, const romis_features* features, co
                               int width, int height, int history_valid, const romis_rng* rng,
                               const float** dev_rgb);
 int romis_synchronize(romis_ctx* ctx);
+/* Largest c (with margin) such that pow(x, shininess) as this path evaluates it (include/romis_detmath.h) is +-0 or NaN for
+ * every |x| <= c, or 0 when no such bound >= 0.05 exists: outside that lobe computeShading's specular term (reference
+ * src/rendering/shading.cpp:21-28) is exactly zero and the kernels skip it.  Pure function, no context; exported so
+ * that the tests can check the claim against the oracle's pow. */
+float romis_specular_cutoff(float shininess);
 
 /* One R-MIS frame = renderRMIS (render.cpp:64-119): primary hits, a neighbour index grid (k neighbours per pixel within the
  * spatial radius: random, or chosen by similarity of depth / normal / geometry, neighbour_selection.cpp), then

@@ -25,7 +25,7 @@ EXPORTS = [
     "romis_set_capture", "romis_download_reservoirs", "romis_download_gbuffer", "romis_trace_rays",
     "romis_set_stage_timing", "romis_last_frame_timings", "romis_host_alloc", "romis_host_free",
     "romis_row_hit_counts", "romis_band_prepare", "romis_peer_export", "romis_peer_attach", "romis_peer_detach", "romis_peer_error",
-    "romis_render_frame_rmis", "romis_download_rmis_neighbours",
+    "romis_render_frame_rmis", "romis_download_rmis_neighbours", "romis_specular_cutoff",
 ]
 PEER_BLOB_BYTES = 512
 
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
     L.romis_peer_attach.argtypes = [vp, vp, vp]
     L.romis_peer_detach.argtypes = [vp]
     L.romis_peer_error.argtypes = [vp, C.POINTER(ci)]
+    L.romis_specular_cutoff.restype = C.c_float; L.romis_specular_cutoff.argtypes = [C.c_float]
     L.romis_host_alloc.restype = vp; L.romis_host_alloc.argtypes = [C.c_size_t]
     L.romis_host_free.argtypes = [vp]; L.romis_host_free.restype = None
     _lib = L

@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, fr.initial_stage, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
     ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;               // light.cpp:58-60
-    const float invPdf = 1.0f / (float)sc.n_lights;                                 // light.cpp:80
+    const float nLights = (float)sc.n_lights, invPdf = 1.0f / nLights;              // light.cpp:80
+    // L a power of two (512, 65 536, 2^20 in the BASELINE configs): 1/L is exact and pdf / 2^-k and pdf * 2^k are the same
+    // real number, rounded (or overflowed) once either way: the division is a multiplication
+    const bool pow2L = (sc.n_lights & (sc.n_lights - 1)) == 0 && sc.n_lights <= (1 << 24);
     const uint32_t Mcand = fr.f.initialLightSamples;
     for (uint32_t i = 0; i < Mcand; i++) {
         uint32_t li = (uint32_t)romis_rng_uniform_int(romis_rng_bits(ek, i), 0, sc.n_lights - 1);
@@ -41,8 +44,8 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         v3 pos, col; light_sample(sc.lights, li, u, v, pos, col);
         float pdf = target_pdf(c, es, pos, col);
         float w = 0.0f;                                     // +0 / (1/L) = +0: keep 0 / x off the slow division path
-        if (pdf != 0.0f) w = pdf / invPdf;
-        res_update(r, N, li, u, v, w, rk, rc);
+        if (pdf != 0.0f) w = pow2L ? pdf * nLights : pdf / invPdf;
+        res_update(r, N, li, u, v, pdf, w, rk, rc);
     }
     // light.cpp:85-95: visibility reuse zeroes W of occluded samples, otherwise W = (1/pdf)(1/M)wSum
     res_finish(r, N, sc, c, es);

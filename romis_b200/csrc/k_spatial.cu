@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
             }
         }
         ROMIS_FOR_SUB(j, NT, N) {
-            float pdf = target_pdf(c, es, spos[j], scol[j]);
+            float pdf = res_held_pdf(r, j, c, es);
             r.W[j] = (pdf == 0.0f || Z[j] == 0ull) ? 0.0f : (1.0f / pdf) * (1.0f / (float)Z[j]) * r.wSum[j];
         }
     }

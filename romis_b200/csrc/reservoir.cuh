@@ -20,6 +20,7 @@ namespace romis {
 template <int NT> struct SubRes {
     static constexpr int CAP = NT > 0 ? NT : 32;
     uint32_t light[CAP]; float u[CAP], v[CAP], W[CAP], wSum[CAP];
+    float pdf[CAP];     // target pdf of the held sample at THIS pixel, as evaluated when it was accepted (see res_finish)
     uint32_t M[CAP];
     uint64_t cnt[CAP];
 };
@@ -27,12 +28,12 @@ template <int NT> struct SubRes {
 // Reservoir::Reservoir (reservoir.h:29-32)
 template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N) {
     ROMIS_FOR_SUB(j, NT, N) {
-        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull;
+        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull; r.pdf[j] = 0.0f;
     }
 }
 
 // Reservoir::update (reservoir.cpp:10-32); returns the sub-reservoir that took the sample
-template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N, uint32_t light, float u, float v, float weight,
+template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N, uint32_t light, float u, float v, float pdf, float weight,
                                                             romis_stream_key rk, uint32_t& rc) {
     int idx = 0; float smallest = FLT_MAX;
     ROMIS_FOR_SUB(j, NT, N) { if (r.wSum[j] < smallest) { idx = j; smallest = r.wSum[j]; } }
@@ -48,7 +49,7 @@ template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N
             r.M[j] += 1u;
             if (!zero) {
                 r.wSum[j] += weight;
-                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; }
+                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; r.pdf[j] = pdf; }
             }
         }
     }
@@ -62,11 +63,19 @@ template <int NT> __device__ __forceinline__ void res_store(const ResBuf& b, int
     }
 }
 
+// targetPDF of the held sample y_j at this pixel (light.cpp:88, reservoir.cpp:59,98).  The reference evaluates it again
+// here; the sample was accepted by an update whose weight was built from exactly that evaluation (same pixel, same light
+// sample, a pure function), so the value kept at acceptance has the same bits.  A sub-reservoir that never accepted holds
+// the default LightSample (position = colour = 0, reservoir.h:18-21), which is evaluated here.
+template <int NT> __device__ __forceinline__ float res_held_pdf(const SubRes<NT>& r, int j, const PixCtx& c, bool es) {
+    if (r.light[j] == ROMIS_NO_LIGHT) return target_pdf(c, es, V3(0, 0, 0), V3(0, 0, 0));
+    return r.pdf[j];
+}
+
 // W_j = pdf == 0 ? 0 : (1/pdf) * (1/M_j) * wSum_j   (light.cpp:89-93, reservoir.cpp:57-65)
 template <int NT> __device__ __forceinline__ void res_finish(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es) {
     ROMIS_FOR_SUB(j, NT, N) {
-        v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
-        float pdf = target_pdf(c, es, pos, col);
+        float pdf = res_held_pdf(r, j, c, es);
         float Wj = 0.0f;
         if (pdf != 0.0f) Wj = (1.0f / pdf) * (1.0f / (float)r.M[j]) * r.wSum[j];   // a real branch: 1/M with M = 0 stays unevaluated
         r.W[j] = Wj;
@@ -79,7 +88,7 @@ template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, i
     float u = __uint_as_float(rec.y), v = __uint_as_float(rec.z), Wi = __uint_as_float(rec.w);
     v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col);
     float pdf = target_pdf(c, es, pos, col);
-    int idx = res_update(r, N, rec.x, u, v, pdf * Wi * (float)Mi, rk, rc);
+    int idx = res_update(r, N, rec.x, u, v, pdf, pdf * Wi * (float)Mi, rk, rc);
         if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] += (uint64_t)Mi; } }
     else r.cnt[idx] += (uint64_t)Mi;
 }

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -198,6 +199,25 @@ extern "C" int romis_synchronize(romis_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 // scene
 // ------------------------------------------------------------------------------------------------
+// A bound c such that romis_powf(x, shininess) is +-0 (or NaN) for EVERY |x| <= c: computeShading's specular factor
+// pow(cosTheta, shininess) (shading.cpp:26) underflows there, e.g. c = 0.659 for Ns 250.  Found by bisection on the
+// underflow edge of the same romis_powf the kernels call, then pulled in by 0.1 %: x^s <= 0.999^s * 2^-150 is far enough
+// below the rounding boundary for the binary64 evaluation (relative error ~1e-15) to round to zero too.  The device test
+// compares dot(Rraw, V)^2 with c^2 (1 - 1e-4) |Rraw|^2 on the UN-normalised reflection vector; its fp32 roundings and those
+// of the exact route (normalise, dot) are each below 1.5e-6 absolute on |cosTheta|, which the 1e-4 relative margin covers
+// only while c >= 0.05 -- below that (low exponents) the shortcut is off (returns 0).
+extern "C" float romis_specular_cutoff(float shininess) {
+    if (!(shininess >= 1.0f) || !(shininess < 3.0e38f)) return 0.0f;
+    if (romis_powf(0.05f, shininess) != 0.0f) return 0.0f;
+    float lo = 0.05f, hi = 1.0f;                    // pow(lo) == 0, pow(hi) == 1
+    for (int i = 0; i < 64; i++) {
+        const float mid = 0.5f * (lo + hi);
+        if (mid <= lo || mid >= hi) break;
+        if (romis_powf(mid, shininess) == 0.0f) lo = mid; else hi = mid;
+    }
+    return lo * 0.999f;
+}
+
 extern "C" int romis_upload_scene(romis_ctx* c, const romis_mesh_desc* meshes, int n_meshes,
                                   const romis_texture* textures, int n_textures) {
     if (!c) return ROMIS_ERR_INVALID;
@@ -230,18 +250,24 @@ extern "C" int romis_upload_scene(romis_ctx* c, const romis_mesh_desc* meshes, i
     Bvh bvh = build_bvh(verts.data(), (int)ntri);
     if (bvh.max_depth >= ROMIS_STACK) return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: BVH deeper than the traversal stack");
 
-    std::vector<float4> mats(2 * (size_t)(n_meshes + 1));
+    std::vector<float4> mats(3 * (size_t)(n_meshes + 1));
     bool any_tex = false;
     for (int m = 0; m < n_meshes; m++) {
         const romis_material& mt = meshes[m].material;
         int tex = (mt.kd_texture >= 0 && mt.kd_texture < n_textures) ? mt.kd_texture : -1;
         any_tex |= tex >= 0;
-        mats[2 * m] = make_float4(mt.kd[0], mt.kd[1], mt.kd[2], mt.shininess);
-        mats[2 * m + 1] = make_float4(mt.ks[0], mt.ks[1], mt.ks[2], u2f((uint32_t)tex));
+        mats[3 * m] = make_float4(mt.kd[0], mt.kd[1], mt.kd[2], mt.shininess);
+        mats[3 * m + 1] = make_float4(mt.ks[0], mt.ks[1], mt.ks[2], u2f((uint32_t)tex));
+        // ks = 0: the specular term is +-0 (or NaN, zeroed by shading.cpp:28) for every sample; otherwise it is outside the lobe
+        float cut2 = 0.0f;
+        if (mt.ks[0] == 0.0f && mt.ks[1] == 0.0f && mt.ks[2] == 0.0f) cut2 = INFINITY;
+        else { const float cut = romis_specular_cutoff(mt.shininess); cut2 = cut * cut * (1.0f - 1e-4f); }
+        mats[3 * m + 2] = make_float4(cut2, 0, 0, 0);
     }
     // miss pixels carry a value-initialised Material: kd = ks = 0, shininess = 1 (mesh.h:22-34)
-    mats[2 * n_meshes] = make_float4(0, 0, 0, 1.0f);
-    mats[2 * n_meshes + 1] = make_float4(0, 0, 0, u2f(0xffffffffu));
+    mats[3 * n_meshes] = make_float4(0, 0, 0, 1.0f);
+    mats[3 * n_meshes + 1] = make_float4(0, 0, 0, u2f(0xffffffffu));
+    mats[3 * n_meshes + 2] = make_float4(0, 0, 0, 0);
 
     std::vector<float> texpx; std::vector<int4> texdesc((size_t)std::max(1, n_textures));
     for (int t = 0; t < n_textures; t++) {

@@ -66,3 +66,30 @@ def test_rng_streams_are_uniform_and_keyed():
     d = -r + ((bits.astype(np.uint64) * np.uint64(2 * r + 1)) >> np.uint64(32)).astype(np.int64)
     assert d.min() == -r and d.max() == r and np.bincount(d + r).min() > 20000 / 21 * 0.8
     orc.close()
+
+
+def test_specular_cutoff_claim():
+    """romis_specular_cutoff(s) = c promises pow(x, s) in {+-0, NaN} for every |x| <= c (include/romis_gpu.h): checked
+    against the oracle's romis_powf on dense samples of [-c, c], the boundary itself, and just outside for tightness.
+    (Host-only function of libromis_gpu.so: no GPU call.)"""
+    import ctypes
+    from romis_b200.api import load_library
+    lib = load_library()
+    orc = Oracle().lib
+    orc.orc_powf.restype = ctypes.c_float; orc.orc_powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    rng = np.random.default_rng(3)
+    for s in (1.0, 3.5, 10.000004768371582, 32.0, 250.0, 1000.0, 65536.0, 70000.5):
+        c = np.float32(lib.romis_specular_cutoff(ctypes.c_float(s)))
+        if s < 60:                     # 0.05^s must underflow: s log2(20) > 150
+            assert c == 0.0, (s, c)
+            continue
+        assert 0.05 <= c < 1.0
+        xs = np.concatenate([rng.uniform(-c, c, 20000), c * (1 - np.logspace(-7, -1, 2000)), [c, -c, 0.0]]).astype(np.float32)
+        xs = xs[np.abs(xs) <= c]
+        for x in xs:
+            r = np.float32(orc.orc_powf(ctypes.c_float(float(x)), ctypes.c_float(s)))
+            assert r == 0.0 or np.isnan(r), (s, float(x), float(r))
+        # tight to within 0.2 %: just above the bound the lobe is alive
+        assert np.float32(orc.orc_powf(ctypes.c_float(float(c) * 1.002), ctypes.c_float(s))) != 0.0
+    for s in (0.0, -2.0, 0.5, float("nan"), float("inf")):
+        assert lib.romis_specular_cutoff(ctypes.c_float(s)) == 0.0

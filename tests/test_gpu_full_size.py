@@ -62,3 +62,4 @@ def test_full_size_invariants_determinism_and_band_equivalence():
     assert_bits_equal(img, imgs[0], "3 row bands vs single context at 1080p")
     for b in bands:
         b.close()
+

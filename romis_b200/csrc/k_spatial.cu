@@ -44,11 +44,12 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         }
         if (keep) stream[ns++] = ((uint32_t)nrow << 16) | (uint32_t)nx;
     }
-    stream[ns++] = ((uint32_t)lrow << 16) | (uint32_t)x;
     // Phase 2 -- stream the selected reservoirs through Reservoir::update in order (reservoir.cpp:42-53); the records of
-    // entry s+1 are fetched while entry s is being evaluated.
+    // entry s+1 are fetched while entry s is being evaluated.  Self goes last (:124) and outside the loop: every lane of
+    // the warp reaches it together, and its target pdf at this pixel is stored with the record, so the warp skips the
+    // evaluation as a whole.
     uint4 rec[CAP], nrec[CAP]; uint32_t Mi[CAP], nMi[CAP];
-    {
+    if (ns > 0) {
         int srow = (int)(stream[0] >> 16), sx = (int)(stream[0] & 0xffffu);
         ROMIS_FOR_SUB(j, NT, N) { nrec[j] = res_rec(in, srow, j)[sx]; nMi[j] = res_m(in, srow, j)[sx]; }
     }
@@ -60,6 +61,9 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         }
         ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, rec[j], Mi[j], rk, rc);
     }
+    ROMIS_FOR_SUB(j, NT, N) { rec[j] = res_rec(in, lrow, j)[x]; Mi[j] = res_m(in, lrow, j)[x]; }
+    ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, rec[j], Mi[j], rk, rc, res_pdf(in, lrow, j)[x]);
+    stream[ns++] = ((uint32_t)lrow << 16) | (uint32_t)x;       // the unbiased normalisation below walks the whole stream
     res_take_counts(r, N);
     if (!UNBIASED) {
         res_finish(r, N, sc, c, es);
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         }
         ROMIS_FOR_SUB(j, NT, N) {
             float pdf = res_held_pdf(r, j, c, es);
+            r.pdf[j] = pdf;
             r.W[j] = (pdf == 0.0f || Z[j] == 0ull) ? 0.0f : (1.0f / pdf) * (1.0f / (float)Z[j]) * r.wSum[j];
         }
     }

@@ -17,10 +17,10 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
     const int lrow = y - fr.ey0;
     const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
     constexpr int CAP = SubRes<NT>::CAP;
-    uint4 crec[CAP], prec[CAP]; uint32_t cM[CAP], pM[CAP];
+    uint4 crec[CAP], prec[CAP]; uint32_t cM[CAP], pM[CAP]; float cpdf[CAP];
     uint64_t curTotal = 0, prevTotal = 0;
     ROMIS_FOR_SUB(j, NT, N) {
-        crec[j] = res_rec(cur, lrow, j)[x]; cM[j] = res_m(cur, lrow, j)[x];
+        crec[j] = res_rec(cur, lrow, j)[x]; cM[j] = res_m(cur, lrow, j)[x]; cpdf[j] = res_pdf(cur, lrow, j)[x];
         prec[j] = res_rec(prev, lrow, j)[x]; pM[j] = res_m(prev, lrow, j)[x];
         curTotal += cM[j]; prevTotal += pM[j];
     }
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
     romis_stream_key rk = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_TEMPORAL, pixel, ROMIS_STREAM_RAND);
     uint32_t rc = 0;
     SubRes<NT> r; res_init(r, N);
-    ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, crec[j], cM[j], rk, rc);    // :169 current first
+    ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, crec[j], cM[j], rk, rc, cpdf[j]);    // :169 current first (pdf at this pixel known)
         ROMIS_FOR_SUB(j, NT, N) stream_sample(r, N, sc, c, es, prec[j], pM[j], rk, rc);    // then the predecessor
     res_take_counts(r, N);
     res_finish(r, N, sc, c, es);

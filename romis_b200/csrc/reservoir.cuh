@@ -60,6 +60,7 @@ template <int NT> __device__ __forceinline__ void res_store(const ResBuf& b, int
     ROMIS_FOR_SUB(j, NT, N) {
         res_rec(b, lrow, j)[x] = make_uint4(r.light[j], __float_as_uint(r.u[j]), __float_as_uint(r.v[j]), __float_as_uint(r.W[j]));
         res_m(b, lrow, j)[x] = r.M[j];
+        res_pdf(b, lrow, j)[x] = r.pdf[j];
     }
 }
 
@@ -76,20 +77,23 @@ template <int NT> __device__ __forceinline__ float res_held_pdf(const SubRes<NT>
 template <int NT> __device__ __forceinline__ void res_finish(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es) {
     ROMIS_FOR_SUB(j, NT, N) {
         float pdf = res_held_pdf(r, j, c, es);
+        r.pdf[j] = pdf;
         float Wj = 0.0f;
         if (pdf != 0.0f) Wj = (1.0f / pdf) * (1.0f / (float)r.M[j]) * r.wSum[j];   // a real branch: 1/M with M = 0 stays unevaluated
         r.W[j] = Wj;
     }
 }
 
-// One stream entry of combineBiased / combineUnbiased (reservoir.cpp:42-53): w = (pdf * W_i) * float(M_i)
+// One stream entry of combineBiased / combineUnbiased (reservoir.cpp:42-53): w = (pdf * W_i) * float(M_i).
+// own_pdf >= 0: the entry is this pixel's own reservoir of this frame, whose pdf at this pixel is stored with the record.
 template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, int N, const SceneDev& sc, const PixCtx& c, bool es,
-                                                                uint4 rec, uint32_t Mi, romis_stream_key rk, uint32_t& rc) {
+                                                                uint4 rec, uint32_t Mi, romis_stream_key rk, uint32_t& rc, float own_pdf = -1.0f) {
     float u = __uint_as_float(rec.y), v = __uint_as_float(rec.z), Wi = __uint_as_float(rec.w);
-    v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col);
-    float pdf = target_pdf(c, es, pos, col);
+    float pdf;
+    if (own_pdf >= 0.0f && rec.x != ROMIS_NO_LIGHT) pdf = own_pdf;
+    else { v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col); pdf = target_pdf(c, es, pos, col); }
     int idx = res_update(r, N, rec.x, u, v, pdf, pdf * Wi * (float)Mi, rk, rc);
-        if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] += (uint64_t)Mi; } }
+    if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] += (uint64_t)Mi; } }
     else r.cnt[idx] += (uint64_t)Mi;
 }
 

@@ -423,7 +423,7 @@ static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, in
         c->W = W; c->H = H; c->N = N; c->halo = halo; c->y0 = y0; c->y1 = y1;
         c->ey0 = std::max(0, y0 - halo); c->ey1 = std::min(H, y1 + halo);
         const size_t rows = (size_t)(c->ey1 - c->ey0), px = rows * W;
-        c->row_stride = (((size_t)W * 20 * N) + 15) & ~(size_t)15;
+        c->row_stride = (((size_t)W * ROMIS_RES_BYTES * N) + 15) & ~(size_t)15;
         RCHECK(c, c->gb_tn.ensure(px * sizeof(float4)));
         RCHECK(c, c->gb_mesh.ensure(px * sizeof(uint32_t)));
         RCHECK(c, c->gb_uv.ensure(c->sc.has_textures ? px * sizeof(float2) : 16));

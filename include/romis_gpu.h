@@ -95,7 +95,7 @@ typedef struct romis_features {
     float exposure;                         /* common.h:136 */
 } romis_features;
 
-/* ---- R-MIS (renderRMIS, reference src/rendering/render.cpp:64-119): the fields of Features only that mode reads ---- */
+/* ---- R-MIS / R-OMIS (renderRMIS, renderROMIS, reference src/rendering/render.cpp:64-265): the fields of Features only those modes read ---- */
 enum { ROMIS_MIS_EQUAL = 0, ROMIS_MIS_BALANCE = 1 };                                /* MISWeightRMIS, common.h:31-34 */
 enum { ROMIS_NEIGHBOURS_RANDOM = 0, ROMIS_NEIGHBOURS_SIMILAR = 1, ROMIS_NEIGHBOURS_DISSIMILAR = 2,
        ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR = 3 };                             /* NeighbourSelectionStrategy, common.h:36-41 */
@@ -106,6 +106,8 @@ typedef struct romis_rmis_params {
     uint32_t neighbourSameGeometry;                     /* common.h:111 */
     float neighbourMaxDepthDifferenceFraction;          /* common.h:112 */
     float neighbourMaxNormalAngleDifferenceRadians;     /* common.h:113 (compared against the normals' dot product as is, neighbour_selection.cpp:18) */
+    uint32_t useProgressiveROMIS;                       /* common.h:119 (R-OMIS only) */
+    uint32_t progressiveUpdateMod;                      /* common.h:120 (R-OMIS only) */
 } romis_rmis_params;
 
 /* Camera: what Trackball::generateRay needs (reference framework/src/trackball.cpp:75-78,105-114).
@@ -181,6 +183,20 @@ int romis_render_frame_rmis(romis_ctx* ctx, const romis_features* features, cons
 /* Parity read-back of the last R-MIS frame's neighbour grid: xy[H][W][k+1][2] (entry 0 is the pixel itself, unused
  * entries are -1) and count[H][W]. */
 int romis_download_rmis_neighbours(romis_ctx* ctx, int32_t* xy, uint32_t* count);
+
+/* One R-OMIS frame = renderROMIS (render.cpp:121-265), direct estimator: primary hits and neighbour index grid as R-MIS, then
+ * maxIterationsMIS rounds of { initial RIS per pixel; every pixel adds, for each sample of its k+1 neighbourhood pixels, the
+ * scaled column of all k+1 techniques' contribution-weight reciprocals (arbitraryUnbiasedContributionWeightReciprocal,
+ * render_utils.cpp:245-257) to its (k+1)x(k+1) technique matrix and, times the shaded sample, to three contribution vectors },
+ * then per pixel three minimum-norm least-squares solves (Eigen's completeOrthogonalDecomposition().solve, render_utils.h:52;
+ * here include/romis_cod.h) whose components are summed, tone mapped and written in Screen layout.  useProgressiveROMIS is
+ * rejected (not implemented); numNeighboursToSample <= 10; every pixel's window must hold k other pixels (the reference reads
+ * out of bounds otherwise, render.cpp:165).  Whole frame on one context. */
+int romis_render_frame_romis(romis_ctx* ctx, const romis_features* features, const romis_rmis_params* rmis,
+                             const romis_camera* camera, int width, int height, const romis_rng* rng, float* out_rgb);
+/* Parity read-back of the last R-OMIS frame: matrices[H][W][k+1][k+1] (row-major) and contributions[H][W][3][k+1]
+ * (red, green, blue) as accumulated over all iterations. */
+int romis_download_romis_system(romis_ctx* ctx, float* matrices, float* contributions);
 
 /* ---- row-band sharding (one context per GPU) ---- */
 /* This context renders rows [y0, y1) of the height passed to the frame calls.  Pixels, RNG keys and

@@ -155,6 +155,28 @@ class Oracle:
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         return img, xy, cnt
 
+    def render_frame_romis(self, features: Features, rmis: RmisParams, camera: abi.romis_camera, W: int, H: int, seed: int, frame: int):
+        """renderROMIS restated (oracle/restir_oracle.c orc_render_frame_romis).  Returns (image, technique matrices
+        [H, W, k+1, k+1], contribution vectors [H, W, 3, k+1]) -- the latter two as they stand after the last iteration."""
+        f = features.to_abi(); rp = rmis.to_abi(); r = abi.romis_rng(seed, frame, 0)
+        K1 = features.numNeighboursToSample + 1
+        img = np.zeros((H, W, 3), np.float32); A = np.zeros((H, W, K1, K1), np.float32); B = np.zeros((H, W, 3, K1), np.float32)
+        self.lib.orc_render_frame_romis.argtypes = [C.c_void_p, C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params),
+                                                    C.POINTER(abi.romis_camera), C.c_int, C.c_int, C.POINTER(abi.romis_rng),
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.orc_render_frame_romis(self.ctx, C.byref(f), C.byref(rp), C.byref(camera), W, H, C.byref(r),
+                                                    img.ctypes.data, A.ctypes.data, B.ctypes.data))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        return img, A, B
+
+    def cod_solve(self, A: np.ndarray, b: np.ndarray):
+        """One system through include/romis_cod.h: (x, rank)."""
+        A = np.ascontiguousarray(A, np.float32); b = np.ascontiguousarray(b, np.float32); n = len(b)
+        x = np.zeros(n, np.float32); rank = C.c_int()
+        self.lib.orc_cod_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        self._check(self.lib.orc_cod_solve(A.ctypes.data, b.ctypes.data, n, x.ctypes.data, C.byref(rank)))
+        return x, rank.value
+
     def reservoirs(self, pass_id: int) -> ReservoirState:
         st = ReservoirState(self.N, self.H, self.W)
         d = st.as_romis_dump()
@@ -301,6 +323,21 @@ class RefLib:
         self._check(self.lib.ref_render_frame_rmis(C.byref(f), C.byref(rp), C.byref(cd), W, H, C.byref(r), img.ctypes.data,
                                                    xy.ctypes.data if want_neighbours else None, cnt.ctypes.data if want_neighbours else None))
         return img, xy, cnt
+
+    def render_frame_romis(self, features: Features, rmis: RmisParams, camera: Camera, W: int, H: int, seed: int, frame: int,
+                           capture: bool = True):
+        """renderROMIS (reference src/rendering/render.cpp:121-265), called whole.  Returns (image, technique matrices,
+        contribution vectors); the latter two come through the visualiseAlphas hook of the harness (None without capture)."""
+        f = features.to_abi(); rp = rmis.to_abi(); r = abi.romis_rng(seed, frame, 0); cd = self._cam(camera)
+        K1 = features.numNeighboursToSample + 1
+        img = np.zeros((H, W, 3), np.float32)
+        A = np.zeros((H, W, K1, K1), np.float32) if capture else None
+        B = np.zeros((H, W, 3, K1), np.float32) if capture else None
+        self.lib.ref_render_frame_romis.argtypes = [C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params), C.POINTER(_ref_camera_desc),
+                                                    C.c_int, C.c_int, C.POINTER(abi.romis_rng), C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.ref_render_frame_romis(C.byref(f), C.byref(rp), C.byref(cd), W, H, C.byref(r), img.ctypes.data,
+                                                    A.ctypes.data if capture else None, B.ctypes.data if capture else None))
+        return img, A, B
 
     def render_frame(self, features: Features, camera: Camera, W: int, H: int, history_valid: bool, seed: int, frame: int,
                      flags: int = 0, dump: bool = True, want_image: bool = True) -> RefFrame:

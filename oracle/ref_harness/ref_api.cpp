@@ -88,6 +88,25 @@ void dumpGrid(const ReservoirGrid& grid, int W, int H, int N, ref_reservoir_dump
 struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
 }
 
+// ---- capture hook: renderROMIS calls visualiseAlphas after every iteration when saveAlphasVisualisation is set
+// (render.cpp:227-229); the reference's own definition is compiled under another name (oracle/Makefile) ----
+namespace { float* g_cap_matrices = nullptr; float* g_cap_contrib = nullptr; }
+void visualiseAlphas(const MatrixGrid& techniqueMatrices, const VectorGrid& contributionVectorsRed,
+                     const VectorGrid& contributionVectorsGreen, const VectorGrid& contributionVectorsBlue,
+                     const glm::ivec2& windowResolution, const Features& features) {
+    const int W = windowResolution.x, H = windowResolution.y, K1 = (int)features.numNeighboursToSample + 1;
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        const size_t p = size_t(y) * W + x;
+        if (g_cap_matrices) for (int i = 0; i < K1; i++) for (int j = 0; j < K1; j++)
+            g_cap_matrices[(p * K1 + i) * K1 + j] = techniqueMatrices[y][x](i, j);
+        if (g_cap_contrib) for (int i = 0; i < K1; i++) {
+            g_cap_contrib[(p * 3 + 0) * K1 + i] = contributionVectorsRed[y][x](i);
+            g_cap_contrib[(p * 3 + 1) * K1 + i] = contributionVectorsGreen[y][x](i);
+            g_cap_contrib[(p * 3 + 2) * K1 + i] = contributionVectorsBlue[y][x](i);
+        }
+    }
+}
+
 extern "C" {
 
 const char* ref_last_error(void) { return g_err.c_str(); }
@@ -287,6 +306,49 @@ int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, 
         if (s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    return 0;
+}
+
+// renderROMIS itself (reference src/rendering/render.cpp:121-265), called whole
+int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
+                           const romis_rng* rng, float* out_rgb, float* matrices, float* contributions) {
+    if (!g_embree) { g_err = "no scene"; return -1; }
+    try {
+        Features features = toFeatures(*f);
+        features.rayTraceMode = RayTraceMode::ROMIS;
+        features.maxIterationsMIS = rp->maxIterationsMIS;
+        features.neighbourSelectionStrategy = static_cast<NeighbourSelectionStrategy>(rp->neighbourSelectionStrategy);
+        features.neighbourSameGeometry = rp->neighbourSameGeometry != 0;
+        features.neighbourMaxDepthDifferenceFraction = rp->neighbourMaxDepthDifferenceFraction;
+        features.neighbourMaxNormalAngleDifferenceRadians = rp->neighbourMaxNormalAngleDifferenceRadians;
+        features.useProgressiveROMIS = rp->useProgressiveROMIS != 0;
+        features.progressiveUpdateMod = rp->progressiveUpdateMod;
+        features.saveAlphasVisualisation = (matrices || contributions);      // -> the capture hook above
+        Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
+        Screen screen(glm::ivec2(W, H), false);
+        Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
+        camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
+        ShimState& s = g_shim;
+        s.mode = SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
+        s.N = (int)features.numSamplesInReservoir; s.k = (int)features.numNeighboursToSample;
+#ifdef _OPENMP
+        omp_set_num_threads(1);
+#endif
+        NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);
+        s.stage_queue.clear(); s.stage_pos = 0; s.stage = SHIM_STAGE_NONE;
+        s.stage_queue.push_back(SHIM_STAGE_PRIMARY_THEN_NEIGH);                         // genPrimaryRayHits, then the index grid
+        for (uint32_t it = 0; it < features.maxIterationsMIS; it++) {
+            s.stage_queue.push_back(ROMIS_STAGE_RMIS_INITIAL0 + (int)it);               // genInitialSamples
+            s.stage_queue.push_back(SHIM_STAGE_NONE);                                   // the accumulation loop's bar (render.cpp:144)
+        }
+        s.stage_queue.push_back(SHIM_STAGE_NONE);                                       // combineToScreen / the summation loop's bar
+        g_cap_matrices = matrices; g_cap_contrib = contributions;
+        renderROMIS(g_scene, camera, *g_embree, screen, features);
+        g_cap_matrices = nullptr; g_cap_contrib = nullptr;
+        std::cout.rdbuf(old);
+        if (s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
+        if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
+    } catch (const std::exception& e) { g_cap_matrices = nullptr; g_cap_contrib = nullptr; g_err = e.what(); return -1; }
     return 0;
 }
 

@@ -50,6 +50,11 @@ int ref_make_camera(const ref_camera_desc* c, int width, int height, romis_camer
 int ref_reset_history(void);
 int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
                           const romis_rng* rng, float* out_rgb, int32_t* neigh_xy, uint32_t* neigh_count);
+/* renderROMIS (reference src/rendering/render.cpp:121-265), called whole.  matrices: [H][W][K1][K1] row-major (K1 = k + 1),
+ * contributions: [H][W][3][K1] (red, green, blue), both as they stand after the LAST iteration (captured through the
+ * visualiseAlphas call of render.cpp:228); any pointer may be NULL. */
+int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
+                           const romis_rng* rng, float* out_rgb, float* matrices, float* contributions);
 int ref_num_threads(void);
 int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
                      const romis_rng* rng, int flags, ref_frame_dump* dump, float* out_rgb, ref_timings* tm);

@@ -25,6 +25,7 @@
 #include "romis_gpu.h"
 #include "romis_rng.h"
 #include "romis_detmath.h"
+#include "romis_cod.h"
 #include "tracer.h"
 
 #define ORC_MAX_N 32
@@ -673,6 +674,133 @@ int orc_render_frame_rmis(orc_ctx* c, const romis_features* f, const romis_rmis_
         }
     }
     free(idx); free(cnt); free(acc);
+    return 0;
+}
+
+/* =============================================================================================== */
+/* R-OMIS (renderROMIS, src/rendering/render.cpp:121-265)                                           */
+/* =============================================================================================== */
+/* arbitraryUnbiasedContributionWeightReciprocal (src/rendering/render_utils.cpp:245-257) */
+static float aucw_reciprocal(const orc_env* e, v3 pos, v3 col, v3 dir, const orc_hit* h, const orc_sub* pixel, int sampleIdx) {
+    float targetPdfValue = target_pdf(e, pos, col, dir, h);
+    if (targetPdfValue == 0.0f) return 0.0f;
+    float mockSampleWeight = targetPdfValue / (1.0f / (float)e->c->nlights);
+    float arbitraryWeight = (1.0f / targetPdfValue) * (1.0f / (float)pixel[sampleIdx].M) *
+                            (pixel[sampleIdx].wSum - pixel[sampleIdx].chosen + mockSampleWeight);
+    return 1.0f / arbitraryWeight;
+}
+
+/* matrices: [H][W][K1][K1], contributions: [H][W][3][K1] after the last iteration (either may be NULL) */
+int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam, int W, int H,
+                           const romis_rng* rng, float* out_rgb, float* matrices, float* contributions) {
+    if (!c->tracer) { strcpy(c->err, "no scene"); return ROMIS_ERR_STATE; }
+    const int N = (int)f->numSamplesInReservoir, k = (int)f->numNeighboursToSample, r = (int)f->spatialResampleRadius;
+    const int K1 = k + 1;
+    if (N < 1 || N > ORC_MAX_N || W < 1 || H < 1 || K1 > ROMIS_COD_MAX) { strcpy(c->err, "bad size"); return ROMIS_ERR_INVALID; }
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR) { strcpy(c->err, "Dissimilar: undefined in the reference"); return ROMIS_ERR_INVALID; }
+    if (rp->useProgressiveROMIS) { strcpy(c->err, "progressive R-OMIS is not restated"); return ROMIS_ERR_INVALID; }
+    /* renderROMIS indexes neighborhood[0 .. k] whatever its size (render.cpp:165,173): every pixel needs k other pixels in
+     * its window, or the reference reads unconstructed Reservoirs */
+    if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM) {
+        long wx = (r + 1 < W ? r + 1 : W), wy = (r + 1 < H ? r + 1 : H);
+        if (wx * wy - 1 < k) { strcpy(c->err, "window smaller than numNeighboursToSample: undefined in the reference"); return ROMIS_ERR_INVALID; }
+    }
+    if (c->W != W || c->H != H || c->N != N) {
+        size_t n = (size_t)W * H;
+        c->gbuf = (orc_hit*)realloc(c->gbuf, n * sizeof(orc_hit));
+        c->cur = (orc_sub*)realloc(c->cur, n * N * sizeof(orc_sub));
+        c->prev = (orc_sub*)realloc(c->prev, n * N * sizeof(orc_sub));
+        c->tmp = (orc_sub*)realloc(c->tmp, n * N * sizeof(orc_sub));
+        c->W = W; c->H = H; c->N = N;
+    }
+    c->have_prev = 0;
+    orc_env env; env.f = f; env.c = c; env.origin = lv(cam->origin);
+    const orc_env* e = &env;
+    primary_hits(c, cam, env.origin, W, H);                                             /* render.cpp:125 */
+    int* idx = (int*)malloc(sizeof(int) * (size_t)W * H * K1);
+    const int win = (2 * r + 1) * (2 * r + 1) + 1;
+    int bad = 0;
+    #pragma omp parallel
+    {
+        int* sim = (int*)malloc(sizeof(int) * (size_t)win); int* dis = (int*)malloc(sizeof(int) * (size_t)win);
+        #pragma omp for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* :126 */
+            size_t p = (size_t)y * W + x;
+            int tmp[ORC_MAX_K + 2];
+            int n = rmis_indices(c, f, rp, rng, x, y, W, H, sim, dis, tmp);
+            if (n != K1) { bad = 1; n = n < K1 ? n : K1; }
+            for (int i = 0; i < K1; i++) idx[p * K1 + i] = i < n ? tmp[i] : 0;
+        }
+        free(sim); free(dis);
+    }
+    if (bad) { free(idx); strcpy(c->err, "a pixel has fewer than k neighbours"); return ROMIS_ERR_INVALID; }
+    float* A = (float*)calloc((size_t)W * H * K1 * K1, sizeof(float));                  /* techniqueMatrices :128 */
+    float* B = (float*)calloc((size_t)W * H * 3 * K1, sizeof(float));                   /* contributionVectors{Red,Green,Blue} :129-131 */
+    for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                            /* :141 */
+        #pragma omp parallel for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* genInitialSamples :143 */
+            size_t p = (size_t)y * W + x;
+            gen_canonical(e, rng, ROMIS_STAGE_RMIS_INITIAL0 + it, (uint32_t)p, gen_ray_dir(cam, x, y, W, H), &c->gbuf[p], &c->cur[p * N]);
+        }
+        #pragma omp parallel for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* :148-222 */
+            size_t p = (size_t)y * W + x;
+            const orc_hit* h = &c->gbuf[p]; v3 dir = gen_ray_dir(cam, x, y, W, H);
+            float* Ap = A + p * K1 * K1; float* Bp = B + p * 3 * K1;
+            for (int a = 0; a < K1; a++) {                                              /* :165 */
+                const orc_sub* px = &c->cur[(size_t)idx[p * K1 + a] * N];
+                for (int j = 0; j < N; j++) {                                           /* :173 */
+                    float colVecW[ROMIS_COD_MAX];
+                    for (int b = 0; b < K1; b++) {                                      /* :178-181 */
+                        int q = idx[p * K1 + b];
+                        colVecW[b] = aucw_reciprocal(e, px[j].pos, px[j].col, gen_ray_dir(cam, q % W, q / W, W, H), &c->gbuf[q],
+                                                     &c->cur[(size_t)q * N], j);
+                    }
+                    v3 sampleColor = visible(e, px[j].pos, dir, h) ? compute_shading(e, px[j].pos, px[j].col, dir, h) : V3(0, 0, 0);   /* :184-186 */
+                    float scaleFactor = FLT_MIN;                                        /* :203-205 */
+                    for (int b = 0; b < K1; b++) scaleFactor += (float)f->numSamplesInReservoir * colVecW[b];
+                    scaleFactor = 1.0f / scaleFactor;
+                    for (int b = 0; b < K1; b++) colVecW[b] *= scaleFactor;             /* :208 */
+                    for (int i = 0; i < K1; i++) for (int b = 0; b < K1; b++) Ap[i * K1 + b] += colVecW[i] * colVecW[b];   /* :209 */
+                    for (int row = 0; row < K1; row++) {                                /* :210-215 */
+                        float scaleColVecConst = scaleFactor * colVecW[row];
+                        Bp[0 * K1 + row] += sampleColor.x * scaleColVecConst;
+                        Bp[1 * K1 + row] += sampleColor.y * scaleColVecConst;
+                        Bp[2 * K1 + row] += sampleColor.z * scaleColVecConst;
+                    }
+                }
+            }
+        }
+    }
+    if (matrices) memcpy(matrices, A, sizeof(float) * (size_t)W * H * K1 * K1);
+    if (contributions) memcpy(contributions, B, sizeof(float) * (size_t)W * H * 3 * K1);
+    if (out_rgb) {                                                                      /* :233-262 */
+        #pragma omp parallel for schedule(guided)
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            size_t p = (size_t)y * W + x;
+            romis_cod cod; float xs[3][ROMIS_COD_MAX];
+            romis_cod_compute(&cod, A + p * K1 * K1, K1);                               /* solveSystem, render_utils.h:52 */
+            for (int ch = 0; ch < 3; ch++) romis_cod_solve(&cod, B + (p * 3 + ch) * K1, xs[ch]);
+            v3 color = V3(0, 0, 0);
+            for (int row = 0; row < K1; row++) { color.x += xs[0][row]; color.y += xs[1][row]; color.z += xs[2][row]; }   /* :247-252 */
+            if (f->enableToneMapping) {
+                v3 mapped = V3(1.0f - romis_expf(f->exposure * -color.x), 1.0f - romis_expf(f->exposure * -color.y), 1.0f - romis_expf(f->exposure * -color.z));
+                float ig = 1.0f / f->gamma;
+                color = V3(romis_powf(mapped.x, ig), romis_powf(mapped.y, ig), romis_powf(mapped.z, ig));
+            }
+            size_t i = (size_t)(H - 1 - y) * W + x;
+            out_rgb[3 * i] = color.x; out_rgb[3 * i + 1] = color.y; out_rgb[3 * i + 2] = color.z;
+        }
+    }
+    free(idx); free(A); free(B);
+    return 0;
+}
+
+/* exported for the solver tests: one system */
+int orc_cod_solve(const float* A, const float* b, int n, float* x, int* rank) {
+    if (n < 1 || n > ROMIS_COD_MAX) return ROMIS_ERR_INVALID;
+    romis_cod cod; romis_cod_compute(&cod, A, n); romis_cod_solve(&cod, b, x);
+    if (rank) *rank = cod.rank;
     return 0;
 }
 

@@ -51,7 +51,8 @@ class romis_features(C.Structure):
 class romis_rmis_params(C.Structure):
     _fields_ = [("maxIterationsMIS", C.c_uint32), ("misWeightRMIS", C.c_uint32), ("neighbourSelectionStrategy", C.c_uint32),
                 ("neighbourSameGeometry", C.c_uint32), ("neighbourMaxDepthDifferenceFraction", C.c_float),
-                ("neighbourMaxNormalAngleDifferenceRadians", C.c_float)]
+                ("neighbourMaxNormalAngleDifferenceRadians", C.c_float),
+                ("useProgressiveROMIS", C.c_uint32), ("progressiveUpdateMod", C.c_uint32)]
 
 
 ROMIS_MIS_EQUAL, ROMIS_MIS_BALANCE = 0, 1

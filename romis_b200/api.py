@@ -26,6 +26,7 @@ EXPORTS = [
     "romis_set_stage_timing", "romis_last_frame_timings", "romis_host_alloc", "romis_host_free",
     "romis_row_hit_counts", "romis_band_prepare", "romis_peer_export", "romis_peer_attach", "romis_peer_detach", "romis_peer_error",
     "romis_render_frame_rmis", "romis_download_rmis_neighbours", "romis_specular_cutoff",
+    "romis_render_frame_romis", "romis_download_romis_system",
 ]
 PEER_BLOB_BYTES = 512
 
@@ -58,6 +59,8 @@ def load_library() -> C.CDLL:
     L.romis_render_frame_rmis.argtypes = [vp, C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params), C.POINTER(abi.romis_camera),
                                           ci, ci, C.POINTER(abi.romis_rng), vp]
     L.romis_download_rmis_neighbours.argtypes = [vp, vp, vp]
+    L.romis_render_frame_romis.argtypes = L.romis_render_frame_rmis.argtypes
+    L.romis_download_romis_system.argtypes = [vp, vp, vp]
     L.romis_frame_spatial_pass.argtypes = [vp, ci]
     L.romis_frame_end.argtypes = [vp, vp]
     L.romis_reset_history.argtypes = [vp]; L.romis_synchronize.argtypes = [vp]
@@ -210,6 +213,25 @@ class RestirRenderer:
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         self._rmis_k1 = features.numNeighboursToSample + 1
         return out
+
+    def render_frame_romis(self, features: Features, rmis: RmisParams, camera, W: int, H: int, seed: int, frame: int,
+                           want_image: bool = True):
+        """renderROMIS (reference src/rendering/render.cpp:121-265), direct estimator.  Returns the float RGB image
+        [H, W, 3] in Screen::pixels() layout, or None with want_image=False (image stays on the device)."""
+        f = features.to_abi(); rp = rmis.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
+        out = np.zeros((H, W, 3), np.float32) if want_image else None
+        self._check(self.lib.romis_render_frame_romis(self.ctx, C.byref(f), C.byref(rp), C.byref(cam), W, H, C.byref(r),
+                                                      out.ctypes.data if want_image else None))
+        self.W, self.H, self.N = W, H, features.numSamplesInReservoir
+        self._rmis_k1 = features.numNeighboursToSample + 1
+        return out
+
+    def romis_system(self):
+        """Technique matrices [H, W, k+1, k+1] and contribution vectors [H, W, 3, k+1] of the last R-OMIS frame."""
+        K1 = self._rmis_k1
+        A = np.zeros((self.H, self.W, K1, K1), np.float32); B = np.zeros((self.H, self.W, 3, K1), np.float32)
+        self._check(self.lib.romis_download_romis_system(self.ctx, A.ctypes.data, B.ctypes.data))
+        return A, B
 
     def rmis_neighbours(self):
         """Neighbour grid of the last R-MIS frame: (xy [H, W, k+1, 2] with -1 for unused entries, count [H, W])."""

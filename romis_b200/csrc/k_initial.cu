@@ -7,8 +7,10 @@ namespace romis {
 // ------------------------------------------------------------------------------------------------
 // initial RIS: M candidates per pixel, + visibility reuse
 // ------------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out) {
+// EXTRA (R-OMIS): also writes wSums and chosenSampleWeights (reservoir.h:38-41), which
+// arbitraryUnbiasedContributionWeightReciprocal reads (render_utils.cpp:245-257), as N planes each.
+template <int NT, bool EXTRA>
+__global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out, float* __restrict__ wsum, float* __restrict__ chosen) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.y1) return;
@@ -16,7 +18,11 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     const bool es = fr.f.enableShading != 0;
     const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
     SubRes<NT> r; res_init(r, N);
-    if (sc.n_lights == 0) { res_store(out, y - fr.ey0, x, r, N); return; }          // light.cpp:46: M_j stays 1
+    const size_t plane = (size_t)fr.W * fr.H;
+    auto store_extra = [&]() {
+        if (EXTRA) { ROMIS_FOR_SUB(j, NT, N) { wsum[(size_t)j * plane + pixel] = r.wSum[j]; chosen[(size_t)j * plane + pixel] = r.chosen[j]; } }
+    };
+    if (sc.n_lights == 0) { res_store(out, y - fr.ey0, x, r, N); store_extra(); return; }          // light.cpp:46: M_j stays 1
     PixCtx c = make_ctx(sc, fr, g, x, y);
     if (c.miss) {
         // every candidate weighs p^ / (1/L) = 0: wSums never leave FLT_MIN, so sub-reservoir 0 wins every strict-'<'
@@ -24,6 +30,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         ROMIS_FOR_SUB(j, NT, N) r.M[j] = 0u;
         r.M[0] = fr.f.initialLightSamples;
         res_store(out, y - fr.ey0, x, r, N);
+        store_extra();
         return;
     }
     romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, fr.initial_stage, pixel, ROMIS_STREAM_ENGINE);
@@ -56,10 +63,13 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         }
     }
     res_store(out, y - fr.ey0, x, r, N);
+    store_extra();
 }
 
 
-void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out) {
-    ROMIS_DISPATCH_N(N, (initial_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, out)));
+void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
+                    float* wsum, float* chosen) {
+    if (wsum && chosen) { ROMIS_DISPATCH_N(N, (initial_kernel<NT, true><<<grid, block, 0, s>>>(sc, fr, g, out, wsum, chosen))); }
+    else { ROMIS_DISPATCH_N(N, (initial_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, out, nullptr, nullptr))); }
 }
 }  // namespace romis

@@ -5,6 +5,7 @@
 // initial_kernel (k_initial.cu) under the iteration's own random-stream stage.
 #include "reservoir.cuh"
 #include "launch.hpp"
+#include "romis_cod.h"
 
 namespace romis {
 
@@ -193,11 +194,123 @@ __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev 
     rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
 }
 
+// ------------------------------------------------------------------------------------------------
+// R-OMIS (renderROMIS, reference src/rendering/render.cpp:121-265)
+// ------------------------------------------------------------------------------------------------
+// One iteration's accumulation (render.cpp:148-222): for every sample (pixel a of the neighbourhood, sub-reservoir j) the
+// column vector of all k+1 sampling techniques evaluated at that sample
+// (arbitraryUnbiasedContributionWeightReciprocal, render_utils.cpp:245-257), scaled, goes into the pixel's technique
+// matrix (outer product) and, weighted by the shaded sample, into the three contribution vectors.  Matrix and vectors
+// live in global memory as planes over the pixels (coalesced read-modify-write); the accumulation order per element is
+// the reference's: iterations, then a, then j.
+template <int NT>
+__global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.H) return;
+    constexpr int CAP = SubRes<NT>::CAP;
+    const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
+    const int K1 = rm.K1;
+    const bool es = fr.f.enableShading != 0;
+    const size_t p = (size_t)y * fr.W + x;
+    const float nLights = (float)sc.n_lights, invPdf = 1.0f / nLights;
+    const bool pow2L = (sc.n_lights & (sc.n_lights - 1)) == 0 && sc.n_lights <= (1 << 24);     // see initial_kernel
+    const float Nf = (float)fr.f.numSamplesInReservoir;
+    PixCtx c = make_ctx(sc, fr, g, x, y);
+    uint32_t q[ROMIS_COD_MAX];
+    for (int a = 0; a < K1; a++) q[a] = rm.nb[(size_t)a * rm.plane + p];
+    for (int a = 0; a < K1; a++) {                                                  // render.cpp:165
+        const int ay = (int)(q[a] >> 16), ax = (int)(q[a] & 0xffffu);
+        v3 spos[CAP], scol[CAP];
+        ROMIS_FOR_SUB(j, NT, N) {
+            const uint4 rec = res_rec(in, ay, j)[ax];
+            light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), spos[j], scol[j]);
+        }
+        float V[CAP][ROMIS_COD_MAX];                                                // colVecW of every sample of pixel a
+        for (int b = 0; b < K1; b++) {                                              // :178-181, distribution b at all N samples
+            const int by = (int)(q[b] >> 16), bx = (int)(q[b] & 0xffffu);
+            const size_t bp = (size_t)by * fr.W + bx;
+            PixCtx cb = make_ctx(sc, fr, g, bx, by);
+            ROMIS_FOR_SUB(j, NT, N) {
+                float w = 0.0f;
+                const float pdf = target_pdf(cb, es, spos[j], scol[j]);
+                if (pdf != 0.0f) {                                                  // render_utils.cpp:248-256
+                    const float mock = pow2L ? pdf * nLights : pdf / invPdf;
+                    const float Mb = (float)res_m(in, by, j)[bx];
+                    const float arbitraryWeight = (1.0f / pdf) * (1.0f / Mb) *
+                                                  ((rm.wsum[(size_t)j * rm.plane + bp] - rm.chosen[(size_t)j * rm.plane + bp]) + mock);
+                    w = 1.0f / arbitraryWeight;
+                }
+                V[j][b] = w;
+            }
+        }
+        ROMIS_FOR_SUB(j, NT, N) {                                                   // :173
+            // the sample shaded at this pixel (:184-186); a zero result adds (+-0) to the contribution vectors
+            v3 sampleColor = V3(0, 0, 0);
+            if (!c.miss) {
+                const v3 shading = compute_shading(c, es, spos[j], scol[j]);
+                if (!(shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) && visible(sc, c, spos[j])) sampleColor = shading;
+            }
+            float scaleFactor = FLT_MIN;                                            // :203-205
+            for (int b = 0; b < K1; b++) scaleFactor += Nf * V[j][b];
+            scaleFactor = 1.0f / scaleFactor;
+            for (int b = 0; b < K1; b++) V[j][b] *= scaleFactor;                    // :208
+            for (int i = 0; i < K1; i++) {
+                const float vi = V[j][i];
+                for (int b = 0; b < K1; b++) rm.tech[(size_t)(i * K1 + b) * rm.plane + p] += vi * V[j][b];      // :209
+                const float scaleColVecConst = scaleFactor * vi;                    // :211
+                rm.contrib[(size_t)(0 * K1 + i) * rm.plane + p] += sampleColor.x * scaleColVecConst;
+                rm.contrib[(size_t)(1 * K1 + i) * rm.plane + p] += sampleColor.y * scaleColVecConst;
+                rm.contrib[(size_t)(2 * K1 + i) * rm.plane + p] += sampleColor.z * scaleColVecConst;
+            }
+        }
+    }
+}
+
+// The direct estimator's final step (render.cpp:233-262): three minimum-norm least-squares solves per pixel
+// (solveSystem = completeOrthogonalDecomposition().solve, render_utils.h:52 -> include/romis_cod.h), component sums,
+// tone mapping, Screen layout.
+__global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.W || y >= fr.H) return;
+    const int K1 = rm.K1;
+    const size_t p = (size_t)y * fr.W + x;
+    float A[ROMIS_COD_MAX * ROMIS_COD_MAX], b[ROMIS_COD_MAX], xs[ROMIS_COD_MAX];
+    for (int i = 0; i < K1 * K1; i++) A[i] = rm.tech[(size_t)i * rm.plane + p];
+    romis_cod cod;
+    romis_cod_compute(&cod, A, K1);
+    float sum[3];
+    for (int ch = 0; ch < 3; ch++) {
+        for (int i = 0; i < K1; i++) b[i] = rm.contrib[(size_t)(ch * K1 + i) * rm.plane + p];
+        romis_cod_solve(&cod, b, xs);
+        float s = 0.0f;
+        for (int i = 0; i < K1; i++) s += xs[i];                                    // :247-252
+        sum[ch] = s;
+    }
+    v3 color = V3(sum[0], sum[1], sum[2]);
+    if (fr.f.enableToneMapping) {
+        float ig = 1.0f / fr.f.gamma;
+        color = V3(romis_powf(1.0f - romis_expf(fr.f.exposure * -color.x), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.y), ig),
+                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.z), ig));
+    }
+    size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;
+    rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
+}
+
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm) {
     rmis_neighbours_kernel<<<grid, block, 0, s>>>(sc, fr, g, rm);
 }
 void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm) {
     ROMIS_DISPATCH_N(N, (rmis_gather_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rm)));
+}
+void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm) {
+    ROMIS_DISPATCH_N(N, (romis_accumulate_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rm)));
+}
+void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
+    dim3 b(32, 4), gr((fr.W + 31) / 32, (fr.H + 3) / 4);
+    romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb);
 }
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
     rmis_combine_kernel<<<grid, block, 0, s>>>(fr, rm, rgb);

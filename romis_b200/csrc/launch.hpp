@@ -4,7 +4,8 @@
 
 namespace romis {
 void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1);
-void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out);
+void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
+                    float* wsum = nullptr, float* chosen = nullptr);
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                      const ResBuf& cur, const ResBuf& prev, const ResBuf& out);
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
@@ -12,6 +13,8 @@ void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased,
 void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb);
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm);
 void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);
+void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);
+void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb);
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb);
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);

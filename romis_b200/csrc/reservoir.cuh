@@ -20,6 +20,7 @@ namespace romis {
 template <int NT> struct SubRes {
     static constexpr int CAP = NT > 0 ? NT : 32;
     uint32_t light[CAP]; float u[CAP], v[CAP], W[CAP], wSum[CAP];
+    float chosen[CAP];  // chosenSampleWeights (reservoir.cpp:27): only R-OMIS reads it, dead code in every other kernel
     float pdf[CAP];     // target pdf of the held sample at THIS pixel, as evaluated when it was accepted (see res_finish)
     uint32_t M[CAP];
     uint64_t cnt[CAP];
@@ -28,7 +29,7 @@ template <int NT> struct SubRes {
 // Reservoir::Reservoir (reservoir.h:29-32)
 template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N) {
     ROMIS_FOR_SUB(j, NT, N) {
-        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull; r.pdf[j] = 0.0f;
+        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull; r.pdf[j] = 0.0f; r.chosen[j] = 0.0f;
     }
 }
 
@@ -49,7 +50,7 @@ template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N
             r.M[j] += 1u;
             if (!zero) {
                 r.wSum[j] += weight;
-                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; r.pdf[j] = pdf; }
+                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; r.pdf[j] = pdf; r.chosen[j] = weight; }
             }
         }
     }

@@ -18,6 +18,7 @@
 
 #include "romis_gpu.h"
 #include "launch.hpp"
+#define ROMIS_COD_MAX_DIM 11     // include/romis_cod.h ROMIS_COD_MAX
 
 using namespace romis;
 
@@ -79,7 +80,7 @@ struct romis_ctx {
     bool exported = false;
 
     // R-MIS (romis_render_frame_rmis): neighbour grid and accumulator of the last frame
-    DevBuf rmis_nb, rmis_acc;
+    DevBuf rmis_nb, rmis_acc, romis_wsum, romis_chosen, romis_tech, romis_contrib;
     int rmis_W = 0, rmis_H = 0, rmis_K1 = 0;
 
     // parity capture
@@ -169,7 +170,7 @@ extern "C" void romis_destroy(romis_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
-                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc}) b->release();
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib}) b->release();
     romis_peer_detach(c);
     c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
@@ -749,31 +750,57 @@ extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, 
 // ------------------------------------------------------------------------------------------------
 // R-MIS frame (renderRMIS, reference src/rendering/render.cpp:64-119)
 // ------------------------------------------------------------------------------------------------
-extern "C" int romis_render_frame_rmis(romis_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
-                                       int W, int H, const romis_rng* rng, float* out_rgb) {
+// mode 0 = R-MIS (renderRMIS, render.cpp:64-119), mode 1 = R-OMIS (renderROMIS, render.cpp:121-265)
+static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                            int W, int H, const romis_rng* rng, float* out_rgb) {
     if (!c) return ROMIS_ERR_INVALID;
-    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_render_frame_rmis: frame in flight");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "frame in flight");
     if (!rp) return fail(c, ROMIS_ERR_INVALID, "null rmis parameters");
     int rc = validate(c, f, cam, W, H, rng);
     if (rc) return rc;
-    if (c->band_y1 > c->band_y0) return fail(c, ROMIS_ERR_INVALID, "romis_render_frame_rmis: row bands are not supported in R-MIS mode");
+    if (c->band_y1 > c->band_y0) return fail(c, ROMIS_ERR_INVALID, "row bands are not supported in R-MIS / R-OMIS mode");
     if (rp->maxIterationsMIS < 1) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS must be >= 1");
-    if (rp->misWeightRMIS > ROMIS_MIS_BALANCE) return fail(c, ROMIS_ERR_INVALID, "unhandled MIS weight type (render.cpp:99)");
+    if (mode == 0 && rp->misWeightRMIS > ROMIS_MIS_BALANCE) return fail(c, ROMIS_ERR_INVALID, "unhandled MIS weight type (render.cpp:99)");
     if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR)
         return fail(c, ROMIS_ERR_INVALID, "NeighbourSelectionStrategy::Dissimilar is undefined behaviour in the reference (neighbour_selection.cpp:88-93)");
     if (rp->neighbourSelectionStrategy > ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR) return fail(c, ROMIS_ERR_INVALID, "unknown neighbour selection strategy");
     if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM && f->spatialResampleRadius > ROMIS_RMIS_MAX_R)
         return fail(c, ROMIS_ERR_INVALID, "spatialResampleRadius must be <= 30 for similarity-based neighbour selection (ui.cpp:308)");
     if (rp->maxIterationsMIS > 0x7fffffffu - ROMIS_STAGE_RMIS_INITIAL0) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS too large");
+    const int K1 = (int)f->numNeighboursToSample + 1;
+    if (mode == 1) {
+        if (K1 > ROMIS_COD_MAX_DIM) return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample must be <= 10 in R-OMIS mode (ui.cpp:307)");
+        if (rp->useProgressiveROMIS) return fail(c, ROMIS_ERR_INVALID, "the progressive R-OMIS estimator is not implemented (direct estimator only)");
+        // renderROMIS indexes neighborhood[0 .. k] whatever its size (render.cpp:165,173): a window with fewer than k other
+        // pixels makes the reference read unconstructed Reservoirs
+        if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM) {
+            const long long r1 = (long long)f->spatialResampleRadius + 1;
+            if (std::min<long long>(r1, W) * std::min<long long>(r1, H) - 1 < (long long)f->numNeighboursToSample)
+                return fail(c, ROMIS_ERR_INVALID, "the resample window holds fewer than numNeighboursToSample pixels: undefined in the reference (render.cpp:165)");
+        }
+    }
     RCHECK(c, cudaSetDevice(c->device));
     if ((rc = ensure_frame_buffers(c, f, W, H))) return rc;
 
-    const int K1 = (int)f->numNeighboursToSample + 1;
     const size_t px = (size_t)W * H;
     RCHECK(c, c->rmis_nb.ensure(px * K1 * sizeof(uint32_t)));
-    RCHECK(c, c->rmis_acc.ensure(px * sizeof(float4)));
     c->rmis_W = W; c->rmis_H = H; c->rmis_K1 = K1;
-    RmisDev rm; rm.p = *rp; rm.nb = (uint32_t*)c->rmis_nb.p; rm.acc = (float4*)c->rmis_acc.p; rm.K1 = K1; rm.plane = px;
+    RmisDev rm; std::memset(&rm, 0, sizeof rm);
+    rm.p = *rp; rm.nb = (uint32_t*)c->rmis_nb.p; rm.K1 = K1; rm.plane = px;
+    if (mode == 0) {
+        RCHECK(c, c->rmis_acc.ensure(px * sizeof(float4)));
+        rm.acc = (float4*)c->rmis_acc.p;
+        RCHECK(c, cudaMemsetAsync(c->rmis_acc.p, 0, px * sizeof(float4), c->stream));
+    } else {
+        RCHECK(c, c->romis_wsum.ensure(px * c->N * sizeof(float)));
+        RCHECK(c, c->romis_chosen.ensure(px * c->N * sizeof(float)));
+        RCHECK(c, c->romis_tech.ensure(px * K1 * K1 * sizeof(float)));
+        RCHECK(c, c->romis_contrib.ensure(px * 3 * K1 * sizeof(float)));
+        rm.wsum = (float*)c->romis_wsum.p; rm.chosen = (float*)c->romis_chosen.p;
+        rm.tech = (float*)c->romis_tech.p; rm.contrib = (float*)c->romis_contrib.p;
+        RCHECK(c, cudaMemsetAsync(rm.tech, 0, px * K1 * K1 * sizeof(float), c->stream));        // MatrixXf::Zero, VectorXf::Zero (:128-131)
+        RCHECK(c, cudaMemsetAsync(rm.contrib, 0, px * 3 * K1 * sizeof(float), c->stream));
+    }
 
     FrameDev& fr = c->fr;
     fr.cam.origin.x = cam->origin[0]; fr.cam.origin.y = cam->origin[1]; fr.cam.origin.z = cam->origin[2];
@@ -787,25 +814,53 @@ extern "C" int romis_render_frame_rmis(romis_ctx* c, const romis_features* f, co
     RCHECK(c, cudaEventRecord(c->ev_begin, c->stream));
     const dim3 grid = grid_for(W, H);
     const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
-    RCHECK(c, cudaMemsetAsync(c->rmis_acc.p, 0, px * sizeof(float4), c->stream));
-    launch_primary(c->stream, grid, kBlock, c->sc, fr, gbuf(c), 0, H);                      // render.cpp:68
-    launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, gbuf(c), rm);                // :69
+    launch_primary(c->stream, grid, kBlock, c->sc, fr, gbuf(c), 0, H);                      // render.cpp:68 / :125
+    launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, gbuf(c), rm);                // :69 / :126
     c->n_launches += 2;
     RCHECK(c, cudaGetLastError());
-    for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72
+    for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work)); // :74
-        launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
+        if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        else launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
         c->n_launches += 2;
         RCHECK(c, cudaGetLastError());
     }
     fr.initial_stage = ROMIS_STAGE_INITIAL;
-    launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);                 // :118
+    if (mode == 0) launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);  // :118
+    else launch_romis_solve(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);             // :233-262
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
     if (out_rgb) RCHECK(c, cudaMemcpyAsync(out_rgb, c->rgb.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     RCHECK(c, cudaStreamSynchronize(c->stream));
+    return ROMIS_OK;
+}
+
+extern "C" int romis_render_frame_rmis(romis_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                                       int W, int H, const romis_rng* rng, float* out_rgb) {
+    return render_mis_frame(c, 0, f, rp, cam, W, H, rng, out_rgb);
+}
+
+extern "C" int romis_render_frame_romis(romis_ctx* c, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                                        int W, int H, const romis_rng* rng, float* out_rgb) {
+    return render_mis_frame(c, 1, f, rp, cam, W, H, rng, out_rgb);
+}
+
+// Parity read-back of the last R-OMIS frame: matrices[H][W][K1][K1], contributions[H][W][3][K1]
+extern "C" int romis_download_romis_system(romis_ctx* c, float* matrices, float* contributions) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->rmis_K1 || !c->romis_tech.p) return fail(c, ROMIS_ERR_STATE, "romis_download_romis_system: no R-OMIS frame rendered");
+    RCHECK(c, cudaSetDevice(c->device));
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    const size_t px = (size_t)c->rmis_W * c->rmis_H; const int K1 = c->rmis_K1;
+    std::vector<float> t(px * K1 * K1), v(px * 3 * K1);
+    RCHECK(c, cudaMemcpy(t.data(), c->romis_tech.p, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    RCHECK(c, cudaMemcpy(v.data(), c->romis_contrib.p, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < px; p++) {
+        if (matrices) for (int i = 0; i < K1 * K1; i++) matrices[p * K1 * K1 + i] = t[(size_t)i * px + p];
+        if (contributions) for (int i = 0; i < 3 * K1; i++) contributions[p * 3 * K1 + i] = v[(size_t)i * px + p];
+    }
     return ROMIS_OK;
 }
 

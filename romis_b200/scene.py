@@ -64,11 +64,14 @@ class RmisParams:
     neighbourSameGeometry: bool = True
     neighbourMaxDepthDifferenceFraction: float = 0.10
     neighbourMaxNormalAngleDifferenceRadians: float = 0.436332
+    useProgressiveROMIS: bool = False           # R-OMIS only (common.h:119-120)
+    progressiveUpdateMod: int = 1
 
     def to_abi(self) -> abi.romis_rmis_params:
         return abi.romis_rmis_params(int(self.maxIterationsMIS), int(self.misWeightRMIS), int(self.neighbourSelectionStrategy),
                                      int(self.neighbourSameGeometry), float(self.neighbourMaxDepthDifferenceFraction),
-                                     float(self.neighbourMaxNormalAngleDifferenceRadians))
+                                     float(self.neighbourMaxNormalAngleDifferenceRadians), int(self.useProgressiveROMIS),
+                                     int(self.progressiveUpdateMod))
 
 
 @dataclass

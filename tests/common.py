@@ -61,3 +61,18 @@ def stage_ids(features, frame):
         ids += [abi.ROMIS_PASS_SPATIAL0 + p for p in range(min(8, features.spatialResamplingPasses))]
     ids.append(abi.ROMIS_PASS_FINAL)
     return ids
+
+
+def assert_mostly_close(a, b, rel, max_frac, what, floor=1e-6):
+    """All but a fraction `max_frac` of the elements within `rel` relative (denominator floored at `floor`).  For results that
+    go through a rank-revealing solve (R-OMIS): a pivot or rank decision that flips on a last-bit difference moves a few
+    pixels by more than rounding, the rest agree to rounding."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, f"{what}: shape"
+    both_bad = ~np.isfinite(a) & ~np.isfinite(b)
+    with np.errstate(invalid="ignore", over="ignore"):
+        d = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+    bad = ~(d <= rel) & ~both_bad
+    frac = bad.mean()
+    assert frac <= max_frac, f"{what}: {frac:.4%} of {a.size} elements beyond rel {rel} (allowed {max_frac:.2%})"
+    return frac

@@ -43,3 +43,18 @@ RMIS_CASES = {
     "rmis_cornell_esd_equal_r30": ("CornellBoxParallelogramLight", 40, 40, Features(spatialResampleRadius=30, numSamplesInReservoir=5, initialLightSamples=8),
                                    RmisParams(maxIterationsMIS=2, neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR), CORNELL_CAM, 83, 0),
 }
+
+# R-OMIS mode (renderROMIS, reference src/rendering/render.cpp:121-265), direct estimator: same tuple layout as RMIS_CASES
+ROMIS_CASES = {
+    "romis_nightclub_similar": ("CornellNightClub", 36, 27, Features(), RmisParams(maxIterationsMIS=3), NIGHTCLUB_CAM, 89, 0),
+    "romis_nightclub_random_n1": ("CornellNightClub", 32, 24, Features(numSamplesInReservoir=1, numNeighboursToSample=3, spatialResampleRadius=30),
+                                  RmisParams(maxIterationsMIS=2, neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_RANDOM), NIGHTCLUB_CAM, 97, 2),
+    "romis_monkey_esd_k7_n3": ("Monkey", 36, 30, Features(numNeighboursToSample=7, spatialResampleRadius=4, numSamplesInReservoir=3),
+                               RmisParams(maxIterationsMIS=2, neighbourSameGeometry=False,
+                                          neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR), CORNELL_CAM, 101, 0),
+    "romis_cornell_vis_k10_n5": ("CornellBoxParallelogramLight", 28, 28, Features(numNeighboursToSample=10, spatialResampleRadius=6, numSamplesInReservoir=5,
+                                                                                  initialLightSamples=8, initialSamplesVisibilityCheck=True, gamma=2.2),
+                                 RmisParams(maxIterationsMIS=2), CORNELL_CAM, 103, 1),
+    "romis_cube_textured_notonemap": ("CubeTextured", 24, 24, Features(numNeighboursToSample=2, spatialResampleRadius=2, enableToneMapping=False),
+                                      RmisParams(maxIterationsMIS=4, neighbourMaxDepthDifferenceFraction=0.02), CORNELL_CAM, 107, 0),
+}

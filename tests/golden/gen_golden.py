@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from oracle.pyoracle import RefLib, REF_FLAG_SPLIT_SPATIAL, build_ref  # noqa: E402
 from romis_b200 import abi  # noqa: E402
-from cases import CASES, RMIS_CASES, SCENES  # noqa: E402
+from cases import CASES, RMIS_CASES, ROMIS_CASES, SCENES  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -37,6 +37,8 @@ def main():
     for s in SCENES:
         ref.load_prebuilt(s)
         ref.export_scene(s).save(os.path.join(OUT, "scenes", s + ".npz"))
+    if "--romis-only" in sys.argv:
+        return romis_cases(ref)
     only_rmis = "--rmis-only" in sys.argv     # the ReSTIR vectors are left as committed
     for name, (scene, W, H, feat, cam, frames, seed) in ({} if only_rmis else CASES).items():
         ref.load_prebuilt(scene)
@@ -61,6 +63,15 @@ def main():
         img, xy, cnt = ref.render_frame_rmis(feat, rmis, cam, W, H, seed, frame)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), camera=cam_array(ref.make_camera(cam, W, H)), image=img,
                             neighbours=xy.astype(np.int16), count=cnt.astype(np.uint8))
+        print(name, "ok")
+    romis_cases(ref)
+
+
+def romis_cases(ref):
+    for name, (scene, W, H, feat, rmis, cam, seed, frame) in ROMIS_CASES.items():
+        ref.load_prebuilt(scene)
+        img, A, B = ref.render_frame_romis(feat, rmis, cam, W, H, seed, frame)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), camera=cam_array(ref.make_camera(cam, W, H)), image=img, matrices=A, contributions=B)
         print(name, "ok")
 
 

@@ -1,12 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- the ReSTIR frame benchmark (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4k]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c4k|rmis|romis]
 
 A "step" is one ReSTIR frame (renderReSTIR, reference src/rendering/render.cpp:28-62) of the workload:
   c2 (default)  cornell-nightclub, 1920x1080, M=32, N=2, temporal + 3 spatial passes k=5 r=10, visibility reuse
                 (BASELINE.json configs[1], the configuration the metric is quoted on)
 Frame 0 has no temporal history, so warm-up frames establish it; every timed frame runs all seven passes.
+  rmis / romis  the same scene and resolution through the reference's other two estimators:
+                one step = one renderRMIS / renderROMIS frame with the reference's defaults (5 iterations, k=5, r=10,
+                similarity-based neighbours; R-MIS with equal weights, R-OMIS direct estimator).  One GPU.
 
   value  frames/s with everything resident in HBM, device time (CUDA events on the launching stream), image left
          on the device.  For N > 1 the frame is split into N row bands, one process per GPU, reservoir halo rows
@@ -187,6 +190,113 @@ def cpu_baseline_leg(scene, W, H, feat, cam, budget_s=20.0):
             "sample": f"{len(times)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
 
 
+MIS_DEFAULT_STEPS = 10
+
+
+def mis_pass_bytes(mode: str, N: int, K1: int):
+    """Algorithmic bytes per pixel PER ITERATION of the dominant kernel: compulsory reads/writes, every logical
+    array once; S = 20 B per sub-reservoir record, G = 20 B per pixel."""
+    if mode == "rmis":      # gather: own G, K1 grid entries, K1*N neighbour records, accumulator read + write
+        return 20 + 4 * K1 + 20 * K1 * N + 24
+    # accumulate: own G, grid, K1*N records + their wSum/chosen, the K1 distributions' G, technique matrix and 3 vectors RMW
+    return 20 + 4 * K1 + (20 + 8) * K1 * N + 20 * K1 + 8 * (K1 * K1 + 3 * K1)
+
+
+def run_mis(args, mode, rank, world):
+    """R-MIS / R-OMIS frames on one GPU (these modes are not sharded: --gpus N > 1 would be N replicas, not run here)."""
+    import torch
+    from romis_b200.api import PinnedImage, RestirRenderer
+    from romis_b200.scene import RmisParams
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"impl": "ours", "config": {"workload": mode}, "unavailable": "R-MIS / R-OMIS frames are not sharded: run with --gpus 1"}), flush=True)
+        return
+    label, scene, W, H, feat, cam = workload("c2")
+    label = label.split(" M=")[0] + f" {'R-MIS equal weights' if mode == 'rmis' else 'R-OMIS direct estimator'}, 5 iterations, M=32 N=2 k=5 r=10, similar neighbours, visibility reuse"
+    rp = RmisParams()                                   # the reference's defaults (common.h:110-121)
+    K1 = feat.numNeighboursToSample + 1; N = feat.numSamplesInReservoir
+    if args.impl == "reference":
+        from oracle.pyoracle import RefLib
+        ref = RefLib(); ref.set_scene(scene); ref.set_mis_timing(True)
+        div = 8
+        w, h = W // div, H // div
+        scale = (w * h) / float(W * H)
+        fn = ref.render_frame_rmis if mode == "rmis" else ref.render_frame_romis
+        times = []
+        for fr in range(max(1, args.warmup) + args.steps):
+            t0 = time.perf_counter()
+            fn(feat, rp, cam, w, h, SEED, fr, False)
+            if fr >= max(1, args.warmup):
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(times)) / scale; fps = 1e3 / ms; cores = os.cpu_count() or 1
+        sample = f"{w}x{h} frames of the same scene/Features ({scale:.4f} of the pixels), time scaled by pixel count; OpenMP on all {cores} host cores, thread-safe RNG shim"
+        print(json.dumps({"impl": "reference", "metric": f"{mode.upper()} frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": label, "width": W, "height": H},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    r = RestirRenderer(0); r.upload_scene(scene)
+    render = r.render_frame_rmis if mode == "rmis" else r.render_frame_romis
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+
+    def run_steps(n, first, host=False, stage=False):
+        r.set_stage_timing(stage)
+        tot = 0.0; acc = {}
+        for i in range(n):
+            flush.fill_(i & 0xff); torch.cuda.synchronize()
+            if host:
+                scene.lights["c0"][0, 0] = np.float32(0.65 + 1e-4 * ((first + i) % 7)); r.upload_lights(scene.lights)
+                t0 = time.perf_counter(); render(feat, rp, cam, W, H, SEED, first + i, want_image=True); tot += 1e3 * (time.perf_counter() - t0)
+            else:
+                render(feat, rp, cam, W, H, SEED, first + i, want_image=False)
+                t = r.timings(); tot += t.total_ms
+                if stage:
+                    for k in ("primary_ms", "neighbours_ms", "initial_ms", "gather_ms", "resolve_ms"):
+                        acc[k] = acc.get(k, 0.0) + getattr(t, k)
+                    acc["launches"] = t.n_launches
+        return tot, acc
+
+    run_steps(args.warmup, 0)
+    clocks = ClockSampler(0); clocks.start()
+    dev_ms, _ = run_steps(args.steps, args.warmup)
+    stage_ms, st = run_steps(args.steps, args.warmup + args.steps, stage=True)
+    e2e_ms, _ = run_steps(args.steps, args.warmup + 2 * args.steps, host=True)
+    clk = clocks.stop()
+    ms = dev_ms / args.steps; fps = 1e3 / ms
+    iters = rp.maxIterationsMIS
+    peak, peak_src = measured_peak_gbs()
+    g_ms = st["gather_ms"] / args.steps / iters
+    gb = mis_pass_bytes(mode, N, K1)
+    ach = gb * W * H / (g_ms * 1e-3) / 1e9
+    kern = "rmis_gather_kernel" if mode == "rmis" else "romis_accumulate_kernel"
+    line = {"metric": f"{mode.upper()} frames/s", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+            "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the timed region)", "sharding": "single GPU"},
+            "gcandidates_per_s": W * H * feat.initialLightSamples * iters * fps / 1e9,
+            "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": "frames/s", "h2d_bytes_per_step": int(6 * 16 * len(scene.lights) + 256), "d2h_bytes_per_step": int(W * H * 12),
+                    "note": "host wall clock around romis_render_frame_" + mode + " with a host image; lights re-uploaded (one edited) per frame"},
+            "gpu_launches": int(st["launches"] * args.steps), "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_px_per_iteration": gb,
+                         "note": "issue-bound like the ReSTIR passes: " + ("(k+1) N shading evaluations + shadow rays" if mode == "rmis" else "(k+1)^2 N target-pdf evaluations") + " per pixel per iteration",
+                         "stages_ms_per_frame": {k: round(v / args.steps, 4) for k, v in st.items() if k.endswith("_ms")}}}
+    if not args.no_cpu_baseline:
+        from oracle.pyoracle import RefLib
+        ref = RefLib(); ref.set_scene(scene); ref.set_mis_timing(True)
+        w, h = W // 8, H // 8; scale = (w * h) / float(W * H)
+        fn = ref.render_frame_rmis if mode == "rmis" else ref.render_frame_romis
+        fn(feat, rp, cam, w, h, SEED, 0, False)
+        ts = []; t_start = time.perf_counter()
+        while len(ts) < 3 and time.perf_counter() - t_start < 25.0:
+            t0 = time.perf_counter(); fn(feat, rp, cam, w, h, SEED, 1 + len(ts), False); ts.append(time.perf_counter() - t0)
+        cms = 1e3 * float(np.median(ts)) / scale
+        line["cpu_baseline"] = {"value": 1e3 / cms, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                "sample": f"{len(ts)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +312,10 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config in ("rmis", "romis"):
+        if args.steps == 100:
+            args.steps = MIS_DEFAULT_STEPS
+        return run_mis(args, args.config, rank, world)
     label, scene, W, H, feat, cam = workload(args.config)
 
     if args.impl == "reference":

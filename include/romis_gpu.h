@@ -281,9 +281,12 @@ typedef struct romis_timings {          /* device time of the last frame, millis
     int32_t n_spatial;
     int32_t n_launches;                 /* kernels launched for the frame */
     float exchange_ms[8];               /* peer-mapped halo push + wait before each spatial pass (not part of spatial_ms) */
+    /* R-MIS / R-OMIS frames (initial_ms = sum over the iterations): */
+    float neighbours_ms;                /* neighbour index grid */
+    float gather_ms;                    /* R-MIS gather / R-OMIS accumulation, sum over the iterations */
+    float resolve_ms;                   /* R-MIS combineToScreen / R-OMIS per-pixel solves */
 } romis_timings;
-/* Per-stage events are recorded only when enabled (they break the frame's CUDA graph into
- * stream launches); total_ms is always available. */
+/* Per-stage events are recorded only when enabled; total_ms is always available. */
 int romis_set_stage_timing(romis_ctx* ctx, int enable);
 int romis_last_frame_timings(romis_ctx* ctx, romis_timings* out);
 

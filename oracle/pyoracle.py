@@ -324,6 +324,10 @@ class RefLib:
                                                    xy.ctypes.data if want_neighbours else None, cnt.ctypes.data if want_neighbours else None))
         return img, xy, cnt
 
+    def set_mis_timing(self, on: bool):
+        """R-MIS / R-OMIS calls run for timing: thread-safe non-parity random stream, OpenMP on all host cores."""
+        self.lib.ref_set_mis_timing(int(on))
+
     def render_frame_romis(self, features: Features, rmis: RmisParams, camera: Camera, W: int, H: int, seed: int, frame: int,
                            capture: bool = True):
         """renderROMIS (reference src/rendering/render.cpp:121-265), called whole.  Returns (image, technique matrices,

@@ -90,7 +90,7 @@ struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
 
 // ---- capture hook: renderROMIS calls visualiseAlphas after every iteration when saveAlphasVisualisation is set
 // (render.cpp:227-229); the reference's own definition is compiled under another name (oracle/Makefile) ----
-namespace { float* g_cap_matrices = nullptr; float* g_cap_contrib = nullptr; }
+namespace { float* g_cap_matrices = nullptr; float* g_cap_contrib = nullptr; int g_mis_timing = 0; }
 void visualiseAlphas(const MatrixGrid& techniqueMatrices, const VectorGrid& contributionVectorsRed,
                      const VectorGrid& contributionVectorsGreen, const VectorGrid& contributionVectorsBlue,
                      const glm::ivec2& windowResolution, const Features& features) {
@@ -274,10 +274,10 @@ int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, 
         Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
         camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
         ShimState& s = g_shim;
-        s.mode = SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
+        s.mode = g_mis_timing ? SHIM_TIMING : SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
         s.N = (int)features.numSamplesInReservoir; s.k = (int)features.numNeighboursToSample;
 #ifdef _OPENMP
-        omp_set_num_threads(1);
+        omp_set_num_threads(g_mis_timing ? omp_get_num_procs() : 1);
 #endif
         NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);
         const uint32_t K1 = features.numNeighboursToSample + 1U;
@@ -303,11 +303,14 @@ int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, 
         s.stage_queue.push_back(SHIM_STAGE_NONE);                                       // combineToScreen
         renderRMIS(g_scene, camera, *g_embree, screen, features);
         std::cout.rdbuf(old);
-        if (s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
+        if (!g_mis_timing && s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
     return 0;
 }
+
+// 1: ref_render_frame_rmis / _romis run for TIMING: thread-safe non-parity random stream, OpenMP on all host cores
+int ref_set_mis_timing(int on) { g_mis_timing = on != 0; return 0; }
 
 // renderROMIS itself (reference src/rendering/render.cpp:121-265), called whole
 int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
@@ -329,10 +332,10 @@ int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp,
         Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
         camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
         ShimState& s = g_shim;
-        s.mode = SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
+        s.mode = g_mis_timing ? SHIM_TIMING : SHIM_PARITY; s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
         s.N = (int)features.numSamplesInReservoir; s.k = (int)features.numNeighboursToSample;
 #ifdef _OPENMP
-        omp_set_num_threads(1);
+        omp_set_num_threads(g_mis_timing ? omp_get_num_procs() : 1);
 #endif
         NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);
         s.stage_queue.clear(); s.stage_pos = 0; s.stage = SHIM_STAGE_NONE;
@@ -346,7 +349,7 @@ int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp,
         renderROMIS(g_scene, camera, *g_embree, screen, features);
         g_cap_matrices = nullptr; g_cap_contrib = nullptr;
         std::cout.rdbuf(old);
-        if (s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
+        if (!g_mis_timing && s.stage_pos != s.stage_queue.size()) { g_err = "stage queue not consumed"; return -2; }
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
     } catch (const std::exception& e) { g_cap_matrices = nullptr; g_cap_contrib = nullptr; g_err = e.what(); return -1; }
     return 0;

@@ -55,6 +55,7 @@ int ref_render_frame_rmis(const romis_features* f, const romis_rmis_params* rp, 
  * visualiseAlphas call of render.cpp:228); any pointer may be NULL. */
 int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
                            const romis_rng* rng, float* out_rgb, float* matrices, float* contributions);
+int ref_set_mis_timing(int on);
 int ref_num_threads(void);
 int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
                      const romis_rng* rng, int flags, ref_frame_dump* dump, float* out_rgb, ref_timings* tm);

@@ -81,4 +81,5 @@ class romis_gbuffer_dump(C.Structure):
 class romis_timings(C.Structure):
     _fields_ = [("primary_ms", C.c_float), ("initial_ms", C.c_float), ("temporal_ms", C.c_float),
                 ("spatial_ms", C.c_float * 8), ("shade_ms", C.c_float), ("total_ms", C.c_float),
-                ("n_spatial", C.c_int32), ("n_launches", C.c_int32), ("exchange_ms", C.c_float * 8)]
+                ("n_spatial", C.c_int32), ("n_launches", C.c_int32), ("exchange_ms", C.c_float * 8),
+                ("neighbours_ms", C.c_float), ("gather_ms", C.c_float), ("resolve_ms", C.c_float)]

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev s
     v3 color = V3(0, 0, 0);
     // Miss pixels shade to exactly +0 (computeShading is 0, W is 0); a sample with W == 0 adds (+-0) and leaves the sum
     // unchanged whatever its visibility: both skip the shadow ray and the shading without changing a bit.
-    for (int j = 0; j < N && !c.miss; j++) {                                        // render_utils.cpp:56-62
+    _Pragma("unroll 1") for (int j = 0; j < N && !c.miss; j++) {                   // render_utils.cpp:56-62 (rolled: one copy of the shading code)
         uint4 rec = res_rec(in, lrow, j)[x];
         if (__uint_as_float(rec.w) == 0.0f) continue;
         v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
             const int by = (int)(q[b] >> 16), bx = (int)(q[b] & 0xffffu);
             const size_t bp = (size_t)by * fr.W + bx;
             PixCtx cb = make_ctx(sc, fr, g, bx, by);
-            ROMIS_FOR_SUB(j, NT, N) {
+            _Pragma("unroll 1") for (int j = 0; j < N; j++) {      // one copy of the evaluation: the kernel is instruction-cache bound
                 float w = 0.0f;
                 const float pdf = target_pdf(cb, es, spos[j], scol[j]);
                 if (pdf != 0.0f) {                                                  // render_utils.cpp:248-256
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
                 V[j][b] = w;
             }
         }
-        ROMIS_FOR_SUB(j, NT, N) {                                                   // :173
+        _Pragma("unroll 1") for (int j = 0; j < N; j++) {                           // :173
             // the sample shaded at this pixel (:184-186); a zero result adds (+-0) to the contribution vectors
             v3 sampleColor = V3(0, 0, 0);
             if (!c.miss) {

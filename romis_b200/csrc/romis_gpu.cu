@@ -812,23 +812,29 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     c->marks.clear(); c->n_launches = 0; c->timings_pending = true;
     std::memset(&c->last, 0, sizeof c->last);
     RCHECK(c, cudaEventRecord(c->ev_begin, c->stream));
+    RCHECK(c, mark(c, 0, 0));
     const dim3 grid = grid_for(W, H);
     const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
     launch_primary(c->stream, grid, kBlock, c->sc, fr, gbuf(c), 0, H);                      // render.cpp:68 / :125
+    RCHECK(c, mark(c, 1, 0));
     launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, gbuf(c), rm);                // :69 / :126
+    RCHECK(c, mark(c, 7, 0));
     c->n_launches += 2;
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
         launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
+        RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
         else launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        RCHECK(c, mark(c, 9, (int)it));
         c->n_launches += 2;
         RCHECK(c, cudaGetLastError());
     }
     fr.initial_stage = ROMIS_STAGE_INITIAL;
     if (mode == 0) launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);  // :118
     else launch_romis_solve(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);             // :233-262
+    RCHECK(c, mark(c, 10, 0));
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
@@ -921,6 +927,10 @@ extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
                 case 4: if (c->marks[i].idx < 8) t.spatial_ms[c->marks[i].idx] = ms; t.n_spatial = std::max(t.n_spatial, c->marks[i].idx + 1); break;
                 case 5: t.shade_ms = ms; break;
                 case 6: if (c->marks[i].idx < 8) t.exchange_ms[c->marks[i].idx] = ms; break;
+                case 7: t.neighbours_ms = ms; break;
+                case 8: t.initial_ms += ms; break;
+                case 9: t.gather_ms += ms; break;
+                case 10: t.resolve_ms = ms; break;
             }
         }
         t.n_launches = c->n_launches;

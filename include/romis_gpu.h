@@ -184,14 +184,15 @@ int romis_render_frame_rmis(romis_ctx* ctx, const romis_features* features, cons
  * entries are -1) and count[H][W]. */
 int romis_download_rmis_neighbours(romis_ctx* ctx, int32_t* xy, uint32_t* count);
 
-/* One R-OMIS frame = renderROMIS (render.cpp:121-265), direct estimator: primary hits and neighbour index grid as R-MIS, then
+/* One R-OMIS frame = renderROMIS (render.cpp:121-265): primary hits and neighbour index grid as R-MIS, then
  * maxIterationsMIS rounds of { initial RIS per pixel; every pixel adds, for each sample of its k+1 neighbourhood pixels, the
  * scaled column of all k+1 techniques' contribution-weight reciprocals (arbitraryUnbiasedContributionWeightReciprocal,
  * render_utils.cpp:245-257) to its (k+1)x(k+1) technique matrix and, times the shaded sample, to three contribution vectors },
  * then per pixel three minimum-norm least-squares solves (Eigen's completeOrthogonalDecomposition().solve, render_utils.h:52;
- * here include/romis_cod.h) whose components are summed, tone mapped and written in Screen layout.  useProgressiveROMIS is
- * rejected (not implemented); numNeighboursToSample <= 10; every pixel's window must hold k other pixels (the reference reads
- * out of bounds otherwise, render.cpp:165).  Whole frame on one context. */
+ * here include/romis_cod.h) whose components are summed, tone mapped and written in Screen layout (direct estimator).  With
+ * useProgressiveROMIS the solves run before every progressiveUpdateMod-th iteration instead and a running estimate built from
+ * the current alphas is averaged over the iterations (render.cpp:160-200,232).  numNeighboursToSample <= 10; every pixel's
+ * window must hold k other pixels (the reference reads out of bounds otherwise, render.cpp:165).  Whole frame on one context. */
 int romis_render_frame_romis(romis_ctx* ctx, const romis_features* features, const romis_rmis_params* rmis,
                              const romis_camera* camera, int width, int height, const romis_rng* rng, float* out_rgb);
 /* Parity read-back of the last R-OMIS frame: matrices[H][W][k+1][k+1] (row-major) and contributions[H][W][3][k+1]

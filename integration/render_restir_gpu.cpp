@@ -136,10 +136,8 @@ extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame) { g.seed = s
 static thread_local float g_halfW = 0.0f, g_halfH = 0.0f;
 extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight) { g_halfW = halfWidth; g_halfH = halfHeight; }
 
-ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid,
-                                const Scene& scene, const Trackball& camera,
-                                const EmbreeInterface& /*embreeInterface: the GPU path owns its own BVH*/, Screen& screen,
-                                const Features& features) {
+// Context, scene / light upload and camera, common to the three entry points
+static romis_camera prepare(const Scene& scene, const Trackball& camera) {
     if (!g.ctx) {
         int dev = 0;
         if (romis_create(&dev, 1, &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
@@ -148,8 +146,6 @@ ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid
     const size_t sig = geometrySignature(scene);
     if (g.sceneKey != scene.meshes.data() || g.sceneSig != sig) { uploadScene(scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; }
     uploadLights(scene);
-
-    const glm::ivec2 res = screen.resolution();
     romis_camera cam;
     const glm::vec3 pos = camera.position();                                // trackball.cpp:75-78
     const glm::quat q = glm::quat(camera.rotationEulerAngles());            // same expression generateRay uses (trackball.cpp:111)
@@ -157,7 +153,15 @@ ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid
     cam.quat[0] = q.w; cam.quat[1] = q.x; cam.quat[2] = q.y; cam.quat[3] = q.z;
     cam.half_width = g_halfW; cam.half_height = g_halfH;
     if (g_halfH == 0.0f) throw std::runtime_error("romis drop-in: image-plane half extents not set (romis_dropin_set_half_extents)");
+    return cam;
+}
 
+ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid,
+                                const Scene& scene, const Trackball& camera,
+                                const EmbreeInterface& /*embreeInterface: the GPU path owns its own BVH*/, Screen& screen,
+                                const Features& features) {
+    const romis_camera cam = prepare(scene, camera);
+    const glm::ivec2 res = screen.resolution();
     const romis_features f = toPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
     // Screen::pixels() is the row-flipped float RGB framebuffer setPixel writes (screen.cpp:37-43,110-118)
@@ -167,4 +171,46 @@ ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid
     // The reservoir grid lives on the device.  The caller only tests the returned grid for presence and hands a copy back
     // next frame (main.cpp:165), so a 1x1 token is enough to carry "history exists".
     return ReservoirGrid(1, std::vector<Reservoir>(1, Reservoir(features.numSamplesInReservoir)));
+}
+
+// ---- the other two estimators behind renderRayTraced (render.cpp:273-276): replacement bodies for
+//      void renderRMIS (render.h:29-30, render.cpp:64-119) and void renderROMIS (render.h:31-32, render.cpp:121-265) ----
+#ifndef ROMIS_DROPIN_RMIS_NAME
+#define ROMIS_DROPIN_RMIS_NAME renderRMIS
+#endif
+#ifndef ROMIS_DROPIN_ROMIS_NAME
+#define ROMIS_DROPIN_ROMIS_NAME renderROMIS
+#endif
+
+static romis_rmis_params toMisPod(const Features& f) {
+    romis_rmis_params p;
+    p.maxIterationsMIS = f.maxIterationsMIS;
+    p.misWeightRMIS = (uint32_t)f.misWeightRMIS;                            // Equal = 0, Balance = 1 (common.h:31-34)
+    p.neighbourSelectionStrategy = (uint32_t)f.neighbourSelectionStrategy;  // Random, Similar, Dissimilar, EqualSimilarDissimilar (common.h:36-41)
+    p.neighbourSameGeometry = f.neighbourSameGeometry;
+    p.neighbourMaxDepthDifferenceFraction = f.neighbourMaxDepthDifferenceFraction;
+    p.neighbourMaxNormalAngleDifferenceRadians = f.neighbourMaxNormalAngleDifferenceRadians;
+    p.useProgressiveROMIS = f.useProgressiveROMIS;
+    p.progressiveUpdateMod = f.progressiveUpdateMod;
+    return p;
+}
+
+void ROMIS_DROPIN_RMIS_NAME(const Scene& scene, const Trackball& camera, const EmbreeInterface&, Screen& screen, const Features& features) {
+    const romis_camera cam = prepare(scene, camera);
+    const glm::ivec2 res = screen.resolution();
+    const romis_features f = toPod(features);
+    const romis_rmis_params p = toMisPod(features);
+    romis_rng rng { g.seed, g.frame++, 0 };
+    check(romis_render_frame_rmis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, &screen.pixels()[0].x), "romis_render_frame_rmis");
+}
+
+// saveAlphasVisualisation (render.cpp:227-229, BMP dumps of the per-technique alphas) is a debugging aid of the CPU path
+// and is not produced here.
+void ROMIS_DROPIN_ROMIS_NAME(const Scene& scene, const Trackball& camera, const EmbreeInterface&, Screen& screen, const Features& features) {
+    const romis_camera cam = prepare(scene, camera);
+    const glm::ivec2 res = screen.resolution();
+    const romis_features f = toPod(features);
+    const romis_rmis_params p = toMisPod(features);
+    romis_rng rng { g.seed, g.frame++, 0 };
+    check(romis_render_frame_romis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, &screen.pixels()[0].x), "romis_render_frame_romis");
 }

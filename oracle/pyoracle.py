@@ -395,3 +395,12 @@ class DropinLib(RefLib):
         img = np.zeros((H, W, 3), np.float32)
         self._check(self.lib.ref_render_frame_dropin(C.byref(f), C.byref(cd), W, H, int(history_valid), C.byref(r), img.ctypes.data))
         return img
+
+    def render_frame_mis_gpu(self, romis: bool, features: Features, rmis: RmisParams, camera: Camera, W: int, H: int, seed: int, frame: int):
+        """renderRMIS_gpu / renderROMIS_gpu (integration/render_restir_gpu.cpp) on the reference's own objects."""
+        f = features.to_abi(); rp = rmis.to_abi(); r = abi.romis_rng(seed, frame, 0); cd = self._cam(camera)
+        img = np.zeros((H, W, 3), np.float32)
+        self.lib.ref_render_frame_mis_dropin.argtypes = [C.c_int, C.POINTER(abi.romis_features), C.POINTER(abi.romis_rmis_params),
+                                                         C.POINTER(_ref_camera_desc), C.c_int, C.c_int, C.POINTER(abi.romis_rng), C.c_void_p]
+        self._check(self.lib.ref_render_frame_mis_dropin(int(romis), C.byref(f), C.byref(rp), C.byref(cd), W, H, C.byref(r), img.ctypes.data))
+        return img

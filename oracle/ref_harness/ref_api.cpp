@@ -360,6 +360,8 @@ int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp,
 // integration/render_restir_gpu.cpp compiled with -DROMIS_DROPIN_NAME=renderReSTIR_gpu
 ReservoirGrid renderReSTIR_gpu(std::shared_ptr<ReservoirGrid> previousFrameGrid, const Scene& scene, const Trackball& camera,
                                const EmbreeInterface& embreeInterface, Screen& screen, const Features& features);
+void renderRMIS_gpu(const Scene& scene, const Trackball& camera, const EmbreeInterface& embreeInterface, Screen& screen, const Features& features);
+void renderROMIS_gpu(const Scene& scene, const Trackball& camera, const EmbreeInterface& embreeInterface, Screen& screen, const Features& features);
 extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame);
 extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight);
 extern "C" {
@@ -380,6 +382,34 @@ int ref_render_frame_dropin(const romis_features* f, const ref_camera_desc* cam,
         if (!history_valid) prevGpu.reset();
         ReservoirGrid grid = renderReSTIR_gpu(prevGpu, g_scene, camera, *g_embree, screen, features);
         prevGpu = std::make_shared<ReservoirGrid>(grid);                            // main.cpp:165
+        if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    return 0;
+}
+// mode 0: renderRMIS_gpu, 1: renderROMIS_gpu -- the reference's own objects through the GPU bodies of the other two estimators
+int ref_render_frame_mis_dropin(int mode, const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
+                                const romis_rng* rng, float* out_rgb) {
+    if (!g_embree) { g_err = "no scene"; return -1; }
+    try {
+        Features features = toFeatures(*f);
+        features.rayTraceMode = mode ? RayTraceMode::ROMIS : RayTraceMode::RMIS;
+        features.maxIterationsMIS = rp->maxIterationsMIS;
+        features.misWeightRMIS = static_cast<MISWeightRMIS>(rp->misWeightRMIS);
+        features.neighbourSelectionStrategy = static_cast<NeighbourSelectionStrategy>(rp->neighbourSelectionStrategy);
+        features.neighbourSameGeometry = rp->neighbourSameGeometry != 0;
+        features.neighbourMaxDepthDifferenceFraction = rp->neighbourMaxDepthDifferenceFraction;
+        features.neighbourMaxNormalAngleDifferenceRadians = rp->neighbourMaxNormalAngleDifferenceRadians;
+        features.useProgressiveROMIS = rp->useProgressiveROMIS != 0;
+        features.progressiveUpdateMod = rp->progressiveUpdateMod;
+        Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
+        Screen screen(glm::ivec2(W, H), false);
+        Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
+        camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
+        const float halfH = std::tan(glm::radians(cam->fov_deg) / 2.0f);            // trackball.cpp:26-27
+        romis_dropin_set_half_extents(window.getAspectRatio() * halfH, halfH);
+        romis_dropin_set_rng(rng->seed, rng->frame);
+        if (mode) renderROMIS_gpu(g_scene, camera, *g_embree, screen, features);
+        else renderRMIS_gpu(g_scene, camera, *g_embree, screen, features);
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
     return 0;

@@ -698,7 +698,7 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
     const int K1 = k + 1;
     if (N < 1 || N > ORC_MAX_N || W < 1 || H < 1 || K1 > ROMIS_COD_MAX) { strcpy(c->err, "bad size"); return ROMIS_ERR_INVALID; }
     if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR) { strcpy(c->err, "Dissimilar: undefined in the reference"); return ROMIS_ERR_INVALID; }
-    if (rp->useProgressiveROMIS) { strcpy(c->err, "progressive R-OMIS is not restated"); return ROMIS_ERR_INVALID; }
+    if (rp->useProgressiveROMIS && rp->progressiveUpdateMod == 0) { strcpy(c->err, "progressiveUpdateMod == 0: modulo by zero in the reference (render.cpp:160)"); return ROMIS_ERR_INVALID; }
     /* renderROMIS indexes neighborhood[0 .. k] whatever its size (render.cpp:165,173): every pixel needs k other pixels in
      * its window, or the reference reads unconstructed Reservoirs */
     if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM) {
@@ -736,6 +736,12 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
     if (bad) { free(idx); strcpy(c->err, "a pixel has fewer than k neighbours"); return ROMIS_ERR_INVALID; }
     float* A = (float*)calloc((size_t)W * H * K1 * K1, sizeof(float));                  /* techniqueMatrices :128 */
     float* B = (float*)calloc((size_t)W * H * 3 * K1, sizeof(float));                   /* contributionVectors{Red,Green,Blue} :129-131 */
+    /* progressive estimator only (:133-139) */
+    const int progressive = rp->useProgressiveROMIS != 0;
+    float* alpha = (float*)calloc((size_t)W * H * 3 * K1, sizeof(float));               /* alphaVectors{Red,Green,Blue} */
+    v3* fin = (v3*)calloc((size_t)W * H, sizeof(v3));                                   /* finalPixelColors */
+    const int32_t totalSamples = (int32_t)((uint32_t)K1 * f->numSamplesInReservoir);
+    const int32_t fractionOfTotalSamples = (int32_t)(f->numSamplesInReservoir / (uint32_t)K1);     /* integer division, as written (:139) */
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                            /* :141 */
         #pragma omp parallel for schedule(guided)
         for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* genInitialSamples :143 */
@@ -746,8 +752,13 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
         for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {                       /* :148-222 */
             size_t p = (size_t)y * W + x;
             const orc_hit* h = &c->gbuf[p]; v3 dir = gen_ray_dir(cam, x, y, W, H);
-            float* Ap = A + p * K1 * K1; float* Bp = B + p * 3 * K1;
+            float* Ap = A + p * K1 * K1; float* Bp = B + p * 3 * K1; float* Al = alpha + p * 3 * K1;
+            if (progressive && it >= 1u && it % rp->progressiveUpdateMod == 0u) {       /* :160-164 alpha estimates from what has been gathered */
+                romis_cod cod; romis_cod_compute(&cod, Ap, K1);
+                for (int ch = 0; ch < 3; ch++) romis_cod_solve(&cod, Bp + ch * K1, Al + ch * K1);
+            }
             for (int a = 0; a < K1; a++) {                                              /* :165 */
+                if (progressive) fin[p] = add3(fin[p], V3(Al[0 * K1 + a], Al[1 * K1 + a], Al[2 * K1 + a]));     /* :168-170 */
                 const orc_sub* px = &c->cur[(size_t)idx[p * K1 + a] * N];
                 for (int j = 0; j < N; j++) {                                           /* :173 */
                     float colVecW[ROMIS_COD_MAX];
@@ -757,6 +768,15 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
                                                      &c->cur[(size_t)q * N], j);
                     }
                     v3 sampleColor = visible(e, px[j].pos, dir, h) ? compute_shading(e, px[j].pos, px[j].col, dir, h) : V3(0, 0, 0);   /* :184-186 */
+                    if (progressive) {                                                  /* :190-200 */
+                        v3 sumAlphaProducts = V3(0, 0, 0); float sumSampleFractionProducts = FLT_MIN;
+                        for (int b = 0; b < K1; b++) {
+                            sumAlphaProducts = add3(sumAlphaProducts, scale3(V3(Al[0 * K1 + b], Al[1 * K1 + b], Al[2 * K1 + b]), colVecW[b]));
+                            sumSampleFractionProducts += (float)fractionOfTotalSamples * colVecW[b];
+                        }
+                        fin[p] = add3(fin[p], scale3(sub3(div3(sampleColor, sumSampleFractionProducts), div3(sumAlphaProducts, sumSampleFractionProducts)),
+                                                     1.0f / (float)totalSamples));
+                    }
                     float scaleFactor = FLT_MIN;                                        /* :203-205 */
                     for (int b = 0; b < K1; b++) scaleFactor += (float)f->numSamplesInReservoir * colVecW[b];
                     scaleFactor = 1.0f / scaleFactor;
@@ -778,11 +798,14 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
         #pragma omp parallel for schedule(guided)
         for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
             size_t p = (size_t)y * W + x;
-            romis_cod cod; float xs[3][ROMIS_COD_MAX];
-            romis_cod_compute(&cod, A + p * K1 * K1, K1);                               /* solveSystem, render_utils.h:52 */
-            for (int ch = 0; ch < 3; ch++) romis_cod_solve(&cod, B + (p * 3 + ch) * K1, xs[ch]);
             v3 color = V3(0, 0, 0);
-            for (int row = 0; row < K1; row++) { color.x += xs[0][row]; color.y += xs[1][row]; color.z += xs[2][row]; }   /* :247-252 */
+            if (progressive) color = div3(fin[p], (float)rp->maxIterationsMIS);         /* combineToScreen (:232, render_utils.cpp:68-85) */
+            else {
+                romis_cod cod; float xs[3][ROMIS_COD_MAX];
+                romis_cod_compute(&cod, A + p * K1 * K1, K1);                           /* solveSystem, render_utils.h:52 */
+                for (int ch = 0; ch < 3; ch++) romis_cod_solve(&cod, B + (p * 3 + ch) * K1, xs[ch]);
+                for (int row = 0; row < K1; row++) { color.x += xs[0][row]; color.y += xs[1][row]; color.z += xs[2][row]; }   /* :247-252 */
+            }
             if (f->enableToneMapping) {
                 v3 mapped = V3(1.0f - romis_expf(f->exposure * -color.x), 1.0f - romis_expf(f->exposure * -color.y), 1.0f - romis_expf(f->exposure * -color.z));
                 float ig = 1.0f / f->gamma;
@@ -792,7 +815,7 @@ int orc_render_frame_romis(orc_ctx* c, const romis_features* f, const romis_rmis
             out_rgb[3 * i] = color.x; out_rgb[3 * i + 1] = color.y; out_rgb[3 * i + 2] = color.z;
         }
     }
-    free(idx); free(A); free(B);
+    free(idx); free(A); free(B); free(alpha); free(fin);
     return 0;
 }
 

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
     v3 finalColor = V3(0, 0, 0);
     for (int a = 0; a < n; a++) {
         const int qy = (int)(q[a] >> 16), qx = (int)(q[a] & 0xffffu);
-        for (int j = 0; j < N; j++) {
+        _Pragma("unroll 1") for (int j = 0; j < N; j++) {
             const uint4 rec = res_rec(in, qy, j)[qx];
             const float Wj = __uint_as_float(rec.w);
             // W == 0 contributes (+-0) whatever the weight and the visibility: the sum keeps its bits
@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev 
 // matrix (outer product) and, weighted by the shaded sample, into the three contribution vectors.  Matrix and vectors
 // live in global memory as planes over the pixels (coalesced read-modify-write); the accumulation order per element is
 // the reference's: iterations, then a, then j.
-template <int NT>
+// PROG (useProgressiveROMIS, render.cpp:133-139,160-170,188-200): the running estimate additionally takes, per pixel of the
+// neighbourhood, the current alpha components and, per sample, (f - sum_b alpha_b w_b) / sum_b (N / (k+1)) w_b over the total
+// sample count -- with the reference's INTEGER N / (k+1) (:139), i.e. a division by FLT_MIN whenever N < k + 1.
+template <int NT, bool PROG>
 __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -219,7 +222,16 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
     PixCtx c = make_ctx(sc, fr, g, x, y);
     uint32_t q[ROMIS_COD_MAX];
     for (int a = 0; a < K1; a++) q[a] = rm.nb[(size_t)a * rm.plane + p];
+    float Al[PROG ? 3 * ROMIS_COD_MAX : 1];
+    v3 fin = V3(0, 0, 0);
+    const float invTotalSamples = 1.0f / (float)(int32_t)((uint32_t)K1 * fr.f.numSamplesInReservoir);          // :138,199
+    const float fractionOfTotalSamples = (float)(int32_t)(fr.f.numSamplesInReservoir / (uint32_t)K1);           // :139
+    if (PROG) {
+        for (int i = 0; i < 3 * K1; i++) Al[i] = rm.alpha[(size_t)i * rm.plane + p];
+        const float4 f4 = rm.acc[p]; fin = V3(f4.x, f4.y, f4.z);
+    }
     for (int a = 0; a < K1; a++) {                                                  // render.cpp:165
+        if (PROG) fin = add3(fin, V3(Al[0 * K1 + a], Al[1 * K1 + a], Al[2 * K1 + a]));     // :168-170
         const int ay = (int)(q[a] >> 16), ax = (int)(q[a] & 0xffffu);
         v3 spos[CAP], scol[CAP];
         ROMIS_FOR_SUB(j, NT, N) {
@@ -251,6 +263,14 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
                 const v3 shading = compute_shading(c, es, spos[j], scol[j]);
                 if (!(shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) && visible(sc, c, spos[j])) sampleColor = shading;
             }
+            if (PROG) {                                                             // :190-200
+                v3 sumAlphaProducts = V3(0, 0, 0); float sumSampleFractionProducts = FLT_MIN;
+                for (int b = 0; b < K1; b++) {
+                    sumAlphaProducts = add3(sumAlphaProducts, scale3(V3(Al[0 * K1 + b], Al[1 * K1 + b], Al[2 * K1 + b]), V[j][b]));
+                    sumSampleFractionProducts += fractionOfTotalSamples * V[j][b];
+                }
+                fin = add3(fin, scale3(sub3(div3(sampleColor, sumSampleFractionProducts), div3(sumAlphaProducts, sumSampleFractionProducts)), invTotalSamples));
+            }
             float scaleFactor = FLT_MIN;                                            // :203-205
             for (int b = 0; b < K1; b++) scaleFactor += Nf * V[j][b];
             scaleFactor = 1.0f / scaleFactor;
@@ -265,12 +285,14 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
             }
         }
     }
+    if (PROG) rm.acc[p] = make_float4(fin.x, fin.y, fin.z, 0.0f);
 }
 
 // The direct estimator's final step (render.cpp:233-262): three minimum-norm least-squares solves per pixel
 // (solveSystem = completeOrthogonalDecomposition().solve, render_utils.h:52 -> include/romis_cod.h), component sums,
 // tone mapping, Screen layout.
-__global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb) {
+// alphas_only: the progressive estimator's per-iteration update of the alpha vectors (:160-164) instead of the image.
+__global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb, int alphas_only) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fr.W || y >= fr.H) return;
@@ -284,10 +306,12 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
     for (int ch = 0; ch < 3; ch++) {
         for (int i = 0; i < K1; i++) b[i] = rm.contrib[(size_t)(ch * K1 + i) * rm.plane + p];
         romis_cod_solve(&cod, b, xs);
+        if (alphas_only) { for (int i = 0; i < K1; i++) rm.alpha[(size_t)(ch * K1 + i) * rm.plane + p] = xs[i]; continue; }
         float s = 0.0f;
         for (int i = 0; i < K1; i++) s += xs[i];                                    // :247-252
         sum[ch] = s;
     }
+    if (alphas_only) return;
     v3 color = V3(sum[0], sum[1], sum[2]);
     if (fr.f.enableToneMapping) {
         float ig = 1.0f / fr.f.gamma;
@@ -306,11 +330,12 @@ void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const Scen
     ROMIS_DISPATCH_N(N, (rmis_gather_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rm)));
 }
 void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm) {
-    ROMIS_DISPATCH_N(N, (romis_accumulate_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rm)));
+    if (rm.p.useProgressiveROMIS) { ROMIS_DISPATCH_N(N, (romis_accumulate_kernel<NT, true><<<grid, block, 0, s>>>(sc, fr, g, in, rm))); }
+    else { ROMIS_DISPATCH_N(N, (romis_accumulate_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, in, rm))); }
 }
-void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
+void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb, bool alphas_only) {
     dim3 b(32, 4), gr((fr.W + 31) / 32, (fr.H + 3) / 4);
-    romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb);
+    romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb, alphas_only ? 1 : 0);
 }
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
     rmis_combine_kernel<<<grid, block, 0, s>>>(fr, rm, rgb);

@@ -14,7 +14,7 @@ void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& 
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm);
 void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);
 void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);
-void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb);
+void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb, bool alphas_only);
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb);
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);

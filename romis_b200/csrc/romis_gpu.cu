@@ -80,7 +80,7 @@ struct romis_ctx {
     bool exported = false;
 
     // R-MIS (romis_render_frame_rmis): neighbour grid and accumulator of the last frame
-    DevBuf rmis_nb, rmis_acc, romis_wsum, romis_chosen, romis_tech, romis_contrib;
+    DevBuf rmis_nb, rmis_acc, romis_wsum, romis_chosen, romis_tech, romis_contrib, romis_alpha;
     int rmis_W = 0, rmis_H = 0, rmis_K1 = 0;
 
     // parity capture
@@ -170,7 +170,7 @@ extern "C" void romis_destroy(romis_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
-                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib}) b->release();
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib, &c->romis_alpha}) b->release();
     romis_peer_detach(c);
     c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
@@ -770,7 +770,8 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     const int K1 = (int)f->numNeighboursToSample + 1;
     if (mode == 1) {
         if (K1 > ROMIS_COD_MAX_DIM) return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample must be <= 10 in R-OMIS mode (ui.cpp:307)");
-        if (rp->useProgressiveROMIS) return fail(c, ROMIS_ERR_INVALID, "the progressive R-OMIS estimator is not implemented (direct estimator only)");
+        if (rp->useProgressiveROMIS && rp->progressiveUpdateMod == 0)
+            return fail(c, ROMIS_ERR_INVALID, "progressiveUpdateMod must be >= 1 (the reference takes iteration % progressiveUpdateMod, render.cpp:160)");
         // renderROMIS indexes neighborhood[0 .. k] whatever its size (render.cpp:165,173): a window with fewer than k other
         // pixels makes the reference read unconstructed Reservoirs
         if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM) {
@@ -800,6 +801,13 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
         rm.tech = (float*)c->romis_tech.p; rm.contrib = (float*)c->romis_contrib.p;
         RCHECK(c, cudaMemsetAsync(rm.tech, 0, px * K1 * K1 * sizeof(float), c->stream));        // MatrixXf::Zero, VectorXf::Zero (:128-131)
         RCHECK(c, cudaMemsetAsync(rm.contrib, 0, px * 3 * K1 * sizeof(float), c->stream));
+        if (rp->useProgressiveROMIS) {                                                          // :133-137
+            RCHECK(c, c->romis_alpha.ensure(px * 3 * K1 * sizeof(float)));
+            RCHECK(c, c->rmis_acc.ensure(px * sizeof(float4)));
+            rm.alpha = (float*)c->romis_alpha.p; rm.acc = (float4*)c->rmis_acc.p;
+            RCHECK(c, cudaMemsetAsync(rm.alpha, 0, px * 3 * K1 * sizeof(float), c->stream));
+            RCHECK(c, cudaMemsetAsync(rm.acc, 0, px * sizeof(float4), c->stream));
+        }
     }
 
     FrameDev& fr = c->fr;
@@ -826,14 +834,18 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
         launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
-        else launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164
+            launch_romis_solve(c->stream, grid, kBlock, fr, rm, nullptr, true);
+            c->n_launches++;
+        }
+        if (mode == 1) launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
         RCHECK(c, mark(c, 9, (int)it));
         c->n_launches += 2;
         RCHECK(c, cudaGetLastError());
     }
     fr.initial_stage = ROMIS_STAGE_INITIAL;
-    if (mode == 0) launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);  // :118
-    else launch_romis_solve(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);             // :233-262
+    if (mode == 0 || rp->useProgressiveROMIS) launch_rmis_combine(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p);   // :118 / :232
+    else launch_romis_solve(c->stream, grid, kBlock, fr, rm, (float*)c->rgb.p, false);      // :233-262
     RCHECK(c, mark(c, 10, 0));
     c->n_launches++;
     RCHECK(c, cudaGetLastError());

@@ -76,3 +76,13 @@ def assert_mostly_close(a, b, rel, max_frac, what, floor=1e-6):
     frac = bad.mean()
     assert frac <= max_frac, f"{what}: {frac:.4%} of {a.size} elements beyond rel {rel} (allowed {max_frac:.2%})"
     return frac
+
+
+def assert_solve_tolerance(a, b, what):
+    """The R-OMIS image bar.  The per-pixel systems are ill-conditioned by construction (neighbouring techniques are nearly the
+    same distribution: measured cond(A) = 1e5 .. 1e6 at full COD rank), so two correct fp32 solves that differ only in
+    summation order (Eigen's SSE packets vs. front-to-back, include/romis_cod.h) differ by cond * eps ~ 1e-2 in the worst
+    pixels while the technique matrices and contribution vectors going in are bit-identical.  Measured against the reference
+    on the nightclub: 5.6 % of the channels beyond 1e-4, 1.2 % beyond 1e-3, 0.3 % beyond 1e-2, none beyond 1e-1."""
+    assert_mostly_close(a, b, 1e-3, 0.03, what + " (1e-3 tier)")
+    assert_mostly_close(a, b, 1e-1, 0.003, what + " (1e-1 tier)")

@@ -55,6 +55,12 @@ ROMIS_CASES = {
     "romis_cornell_vis_k10_n5": ("CornellBoxParallelogramLight", 28, 28, Features(numNeighboursToSample=10, spatialResampleRadius=6, numSamplesInReservoir=5,
                                                                                   initialLightSamples=8, initialSamplesVisibilityCheck=True, gamma=2.2),
                                  RmisParams(maxIterationsMIS=2), CORNELL_CAM, 103, 1),
+    # progressive estimator (useProgressiveROMIS, render.cpp:133-139,160-200); N >= k + 1, or its integer N / (k + 1) is 0
+    "romis_progressive_nightclub_n3_k2": ("CornellNightClub", 36, 27, Features(numSamplesInReservoir=3, numNeighboursToSample=2, spatialResampleRadius=4),
+                                          RmisParams(maxIterationsMIS=3, useProgressiveROMIS=True), NIGHTCLUB_CAM, 109, 0),
+    "romis_progressive_cornell_n6_k5_mod2": ("CornellBoxParallelogramLight", 28, 28, Features(numSamplesInReservoir=6, initialLightSamples=16),
+                                             RmisParams(maxIterationsMIS=5, useProgressiveROMIS=True, progressiveUpdateMod=2,
+                                                        neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_RANDOM), CORNELL_CAM, 113, 1),
     "romis_cube_textured_notonemap": ("CubeTextured", 24, 24, Features(numNeighboursToSample=2, spatialResampleRadius=2, enableToneMapping=False),
                                       RmisParams(maxIterationsMIS=4, neighbourMaxDepthDifferenceFraction=0.02), CORNELL_CAM, 107, 0),
 }

@@ -6,9 +6,10 @@ import os
 import pytest
 
 from oracle import pyoracle
-from romis_b200.scene import Features
+from romis_b200 import abi
+from romis_b200.scene import Features, RmisParams
 from cases import CORNELL_CAM, NIGHTCLUB_CAM
-from common import assert_bits_equal, load_scene
+from common import assert_bits_equal, assert_solve_tolerance, load_scene
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(pyoracle.DROPIN_SO), reason="oracle/_ref/libromis_dropin.so not built (make -C oracle dropin)")]
@@ -27,3 +28,21 @@ def test_dropin_fills_the_reference_screen_identically(scene_name, cam, feat, W,
         cpu = lib.render_frame(feat, cam, W, H, fr > 0, 314, fr, pyoracle.REF_FLAG_WHOLE_FRAME, dump=False).image
         gpu = lib.render_frame_gpu(feat, cam, W, H, fr > 0, 314, fr)
         assert_bits_equal(gpu, cpu, f"{scene_name} frame {fr}: Screen::pixels() of the GPU drop-in vs the reference's renderReSTIR")
+
+
+def test_dropin_rmis_and_romis_fill_the_reference_screen():
+    """renderRMIS / renderROMIS replaced by their GPU bodies: R-MIS fills the Screen the reference's renderRMIS fills bit for bit;
+    R-OMIS to the solve's tolerance (tests/test_romis_oracle.py)."""
+    lib = pyoracle.DropinLib()
+    lib.set_scene(load_scene("CornellNightClub"))
+    W, H = 64, 36
+    feat = Features(initialSamplesVisibilityCheck=True)
+    for rp in (RmisParams(maxIterationsMIS=2), RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE,
+                                                          neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR)):
+        cpu, _xy, _cnt = lib.render_frame_rmis(feat, rp, NIGHTCLUB_CAM, W, H, 2718, 1, False)
+        gpu = lib.render_frame_mis_gpu(False, feat, rp, NIGHTCLUB_CAM, W, H, 2718, 1)
+        assert_bits_equal(gpu, cpu, "Screen::pixels() of the GPU renderRMIS vs the reference's")
+    rp = RmisParams(maxIterationsMIS=2)
+    cpu, _A, _B = lib.render_frame_romis(feat, rp, NIGHTCLUB_CAM, W, H, 2718, 2, False)
+    gpu = lib.render_frame_mis_gpu(True, feat, rp, NIGHTCLUB_CAM, W, H, 2718, 2)
+    assert_solve_tolerance(gpu, cpu, "Screen::pixels() of the GPU renderROMIS vs the reference's")

@@ -424,7 +424,9 @@ def main():
     # DRAM traffic per launch from the committed ncu --set full capture of this same command (profiles/): only meaningful for
     # the configuration and GPU count it was taken on
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+    tpath = os.path.join(ROOT, "profiles", tfiles[-1]) if tfiles else ""          # the newest committed capture
+    tj = {}
     if world == 1 and os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("config") == args.config:
@@ -437,7 +439,7 @@ def main():
                     traffic[name] = per_pass[name]["dram_traffic_bytes"]
     dominant = max(per_pass, key=lambda k: per_pass[k]["ms_per_launch"] * (stages.get("n_spatial", 1) if k == "spatial" else 1))
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": per_pass[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_pass[dominant]["frac"], "traffic": traffic.get(dominant), "traffic_source": "profiles/r01c_summary.md (ncu --set full)" if traffic else None,
+                "frac": per_pass[dominant]["frac"], "traffic": traffic.get(dominant), "traffic_source": (tj.get("source") if traffic else None),
                 "peak_source": peak_src,
                 "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the pass kernels are issue-bound by the parity-exact fp32/fp64 arithmetic, see DESIGN.md",
                 "passes": per_pass}

@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/quick_bench.py 2>&1 | tail -1
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+python tools/quick_bench.py 2>&1 | tail -2

@@ -32,13 +32,18 @@ rows = list(csv.reader(io.StringIO(raw)))
 h, units = rows[0], rows[1]
 lines = [f"# {title}", "", f"Source: `{rep}` (ncu --set full --clock-control none), launch list `{launches}`.", ""]
 lines += ["## Launch list (gpu__time_duration.sum; cold-cache, serialised: compare shares)", "", "| kernel | launches | mean us | share |", "|---|---|---|---|"]
-lr = list(csv.reader(open(launches)))
-hi = [i for i, r in enumerate(lr) if r and r[0] == "ID"][0]
-lh = lr[hi]
 agg = collections.OrderedDict()
-for r in lr[hi + 1:]:
-    if len(r) > lh.index("Metric Value"):
-        agg.setdefault(r[lh.index("Kernel Name")].split("(")[0], []).append(float(r[lh.index("Metric Value")].replace(",", "")))
+if launches != "-":
+    lr = list(csv.reader(open(launches)))
+    hi = [i for i, r in enumerate(lr) if r and r[0] == "ID"][0]
+    lh = lr[hi]
+    for r in lr[hi + 1:]:
+        if len(r) > lh.index("Metric Value"):
+            agg.setdefault(r[lh.index("Kernel Name")].split("(")[0], []).append(float(r[lh.index("Metric Value")].replace(",", "")))
+else:       # no separate launch list: the captured launches themselves
+    for r in rows[2:]:
+        agg.setdefault(r[h.index("Kernel Name")].split("(")[0], []).append(
+            float(r[h.index("gpu__time_duration.sum")].replace(",", "")) * {"us": 1e3, "ms": 1e6, "ns": 1.0}.get(units[h.index("gpu__time_duration.sum")], 1.0))
 tot = sum(sum(v) for v in agg.values())
 for k, v in agg.items():
     lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {100 * sum(v) / tot:.1f}% |")

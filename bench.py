@@ -332,6 +332,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=device)
     r = RestirRenderer(local_rank)
     r.upload_scene(scene)

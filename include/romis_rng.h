@@ -87,7 +87,13 @@ ROMIS_RNG_HD int32_t romis_rng_rand(romis_stream_key k, uint32_t counter) {
 
 /* linearMap(float(rand()), 0, RAND_MAX, 0, 1) with RAND_MAX = 2147483647 -> float 2147483648.0f */
 ROMIS_RNG_HD float romis_rand_to_unit(int32_t r) {
+#if defined(__CUDA_ARCH__)
+    /* Same bits with one multiplication: r >= 0, so float(r) is +0 or >= 1; dividing by 2^31 and multiplying by 2^-31 are
+     * both exact; x - 0, x * 1 and, for x >= +0, x + 0 return x.  (nvcc keeps the `+ 0.0f` otherwise: it cannot know x != -0.) */
+    return (float)r * 4.656612873077392578125e-10f;
+#else
     return (((float)r - 0.0f) / (2147483648.0f - 0.0f)) * (1.0f - 0.0f) + 0.0f;
+#endif
 }
 
 /* uniform integer in [a, b] from one 32-bit draw */

@@ -16,7 +16,7 @@ from . import abi
 from .scene import Camera, Features, RmisParams, Scene, LIGHT_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libromis_gpu.so")
+LIB_PATH = os.environ.get("ROMIS_GPU_LIB") or os.path.join(HERE, "libromis_gpu.so")      # override: tuning builds only
 
 EXPORTS = [
     "romis_abi_version", "romis_create", "romis_destroy", "romis_last_error", "romis_upload_scene", "romis_upload_lights",

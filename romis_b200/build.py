@@ -25,6 +25,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 if os.environ.get("ROMIS_LEAF_MAX"):   # tuning knob, see bvh.cpp
     FLAGS.append("-DROMIS_LEAF_MAX=" + os.environ["ROMIS_LEAF_MAX"])
+if os.environ.get("ROMIS_DEFS"):       # tuning knob: extra -D flags, space separated
+    FLAGS += ["-D" + d for d in os.environ["ROMIS_DEFS"].split()]
+if os.environ.get("ROMIS_LIB_OUT"):    # tuning builds go next to the objects, the product stays libromis_gpu.so
+    LIB = os.environ["ROMIS_LIB_OUT"]
 if os.environ.get("ROMIS_MINB"):       # tuning knob, see device_common.cuh
     FLAGS.append("-DROMIS_MINB=" + os.environ["ROMIS_MINB"])
 

@@ -11,8 +11,8 @@ namespace romis {
 // arbitraryUnbiasedContributionWeightReciprocal reads (render_utils.cpp:245-257), as N planes each.
 template <int NT, bool EXTRA>
 __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out, float* __restrict__ wsum, float* __restrict__ chosen) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;

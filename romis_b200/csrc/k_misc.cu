@@ -8,8 +8,8 @@ namespace romis {
 // primary rays -> G-buffer (band rows plus halo rows)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, GBufDev g, int row0, int row1) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
+    y += row0;
     if (x >= fr.W || y >= row1) return;
     v3 d = gen_ray_dir(fr.cam, x, y, fr.W, fr.H);
     float t, u, v; uint32_t tri;
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, 
 // ------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* __restrict_
 // unpack a reservoir buffer into the flat arrays of romis_reservoir_dump (parity read-back)
 __global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, uint32_t* light, float* u, float* v, float* W, uint32_t* M,
                             float* pos, float* col) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     for (int j = 0; j < N; j++) {
         uint4 rec = res_rec(in, y - fr.ey0, j)[x];

@@ -75,8 +75,7 @@ __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32
 
 // generateResampleIndicesGrid: indicesRandom (neighbour_selection.cpp:24-45) / indicesSimilarity (:47-105)
 __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, FrameDev fr, GBufDev g, RmisDev rm) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<true>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     const int k = (int)fr.f.numNeighboursToSample, r = (int)fr.f.spatialResampleRadius;
     const size_t p = (size_t)y * fr.W + x;
@@ -133,8 +132,7 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
 // point, each weighted by the MIS weight and the sample's outputWeight, with a shadow ray per sample.
 template <int NT>
 __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
@@ -179,8 +177,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
 
 // combineToScreen (render_utils.cpp:68-85): average over the iterations, tone map, Screen layout
 __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     const float4 acc = rm.acc[(size_t)y * fr.W + x];
     v3 color = div3(V3(acc.x, acc.y, acc.z), (float)rm.p.maxIterationsMIS);
@@ -208,8 +205,7 @@ __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev 
 // sample count -- with the reference's INTEGER N / (k+1) (:139), i.e. a division by FLT_MIN whenever N < k + 1.
 template <int NT, bool PROG>
 __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     constexpr int CAP = SubRes<NT>::CAP;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
@@ -293,8 +289,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
 // tone mapping, Screen layout.
 // alphas_only: the progressive estimator's per-iteration update of the alpha vectors (:160-164) instead of the image.
 __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb, int alphas_only) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     const int K1 = rm.K1;
     const size_t p = (size_t)y * fr.W + x;

@@ -9,8 +9,8 @@ namespace romis {
 // ------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = fr.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;

@@ -43,16 +43,31 @@ template <int NT> __device__ __forceinline__ int res_update(SubRes<NT>& r, int N
     // keeps 0 / x off nvcc's slow IEEE-division path (FCHK rejects a zero numerator).
     const bool zero = weight == 0.0f;
     const uint32_t draw = rc++;                                     // reservoir.cpp:24: one rand() per update, always
-    float rnd = 2.0f;
-    if (!zero) rnd = romis_rand_to_unit(romis_rng_rand(rk, draw));
-    ROMIS_FOR_SUB(j, NT, N) {                                       // predicated writes keep the arrays in registers
-        if (j == idx) {
-            r.M[j] += 1u;
-            if (!zero) {
-                r.wSum[j] += weight;
-                if (rnd < (weight / r.wSum[j])) { r.light[j] = light; r.u[j] = u; r.v[j] = v; r.pdf[j] = pdf; r.chosen[j] = weight; }
-            }
+    if (NT > 0) {
+        // The chosen sub-reservoir differs from lane to lane: its wSum is selected into one register first so that the warp
+        // runs ONE addition, division and accept test (a branch per sub-reservoir made it run them once per distinct idx),
+        // then predicated writes put the results back (and keep the arrays in registers).
+        float ws = r.wSum[0];
+        ROMIS_FOR_SUB(j, NT, N) { if (j > 0 && j == idx) ws = r.wSum[j]; }
+        bool accept = false;
+        if (!zero) {
+            const float rnd = romis_rand_to_unit(romis_rng_rand(rk, draw));
+            ws += weight;
+            accept = rnd < (weight / ws);
         }
+        ROMIS_FOR_SUB(j, NT, N) {
+            const bool me = j == idx;
+            r.M[j] += me ? 1u : 0u;
+            if (me) r.wSum[j] = ws;                                 // zero weight: ws is the value it already holds
+            if (me && accept) { r.light[j] = light; r.u[j] = u; r.v[j] = v; r.pdf[j] = pdf; r.chosen[j] = weight; }
+        }
+        return idx;
+    }
+    r.M[idx] += 1u;                                                 // generic N: sub-reservoirs in local memory
+    if (!zero) {
+        const float rnd = romis_rand_to_unit(romis_rng_rand(rk, draw));
+        r.wSum[idx] += weight;
+        if (rnd < (weight / r.wSum[idx])) { r.light[idx] = light; r.u[idx] = u; r.v[idx] = v; r.pdf[idx] = pdf; r.chosen[idx] = weight; }
     }
     return idx;
 }

@@ -1,6 +1,3 @@
-python bench.py --config c4k --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/bench_c4k_n1.json 2>/dev/null; python -c "
-import json; d=json.loads(open('gpurun_out/bench_c4k_n1.json').read().strip().splitlines()[-1]); print('c4k N=1', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
-python bench.py --config c3 --steps 10 --warmup 4 --no-cpu-baseline > gpurun_out/bench_c3_n1.json 2>/dev/null; python -c "
-import json; d=json.loads(open('gpurun_out/bench_c3_n1.json').read().strip().splitlines()[-1]); print('c3 N=1', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], {k:v['ms_per_launch'] for k,v in d['roofline']['passes'].items()})"
-python bench.py --config c4 --steps 63 --warmup 4 --no-cpu-baseline > gpurun_out/bench_c4_n1.json 2>/dev/null; python -c "
-import json; d=json.loads(open('gpurun_out/bench_c4_n1.json').read().strip().splitlines()[-1]); print('c4 N=1', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
+for v in tw4 tw16; do echo $v; ROMIS_GPU_LIB=romis_b200/build/lib_$v.so python tools/quick_bench.py 2>&1 | tail -1; done
+echo default; python tools/quick_bench.py 2>&1 | tail -1
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_rmis.py tests/test_gpu_romis.py -m gpu -x -q 2>&1 | tail -3

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- the ReSTIR frame benchmark (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c4k|rmis|romis]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c2u|c3|c4|c4k|rmis|romis]
 
 A "step" is one ReSTIR frame (renderReSTIR, reference src/rendering/render.cpp:28-62) of the workload:
   c2 (default)  cornell-nightclub, 1920x1080, M=32, N=2, temporal + 3 spatial passes k=5 r=10, visibility reuse
@@ -64,6 +64,10 @@ def workload(name: str):
         s = Scene.load(os.path.join(SCENES, "CornellNightClub.npz"))
         return ("cornell-nightclub 3840x2160 M=32 N=2 temporal + 3 spatial k=5 r=10, visibility reuse", s, 3840, 2160,
                 Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True), Camera())
+    if name == "c2u":    # combineUnbiased + spatialReuseVisibilityCheck, (k+1)*N more shadow rays per pixel and pass
+        label, s, W, H, f, cam = workload("c2")
+        f.unbiasedCombination = True; f.spatialReuseVisibilityCheck = True
+        return (label.replace("visibility reuse", "visibility reuse, unbiased combination with spatial visibility"), s, W, H, f, cam)
     if name == "c4":     # the 64-frame orbit: same as c2 with the camera moving every frame (see camera_for_frame)
         label, s, W, H, f, cam = workload("c2")
         return (label + ", camera orbiting 360 deg / 64 frames", s, W, H, f, cam)

@@ -128,6 +128,17 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
     for (; no < rm.K1; no++) col[(size_t)no * rm.plane] = 0xffffffffu;
 }
 
+// Hit point and unit view vector of every pixel, once per frame (GBufDev::pv): exactly make_ctx's arithmetic.
+__global__ void __launch_bounds__(256) ctx_kernel(SceneDev sc, FrameDev fr, GBufDev g) {
+    int x, y; thread_pixel<false>(x, y);
+    if (x >= fr.W || y >= fr.H) return;
+    GBufDev g0 = g; g0.pv = nullptr;
+    const PixCtx c = make_ctx<false>(sc, fr, g0, x, y);
+    const size_t p = (size_t)y * fr.W + x;
+    g.pv[2 * p] = make_float4(c.P.x, c.P.y, c.P.z, 0.0f);
+    g.pv[2 * p + 1] = make_float4(c.Vv.x, c.Vv.y, c.Vv.z, 0.0f);
+}
+
 // One iteration's gather (render.cpp:79-112): every pixel shades the samples of its neighbourhood pixels at ITS OWN hit
 // point, each weighted by the MIS weight and the sample's outputWeight, with a shadow ray per sample.
 template <int NT>
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
                 float denominator = FLT_MIN;
                 for (int b = 0; b < n; b++) {
                     const int by = (int)(q[b] >> 16), bx = (int)(q[b] & 0xffffu);
-                    PixCtx cb = make_ctx(sc, fr, g, bx, by);
+                    PixCtx cb = make_ctx<true>(sc, fr, g, bx, by);
                     denominator += target_pdf(cb, es, pos, col);
                 }
                 misWeight = numerator / denominator;
@@ -215,9 +226,20 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
     const float nLights = (float)sc.n_lights, invPdf = 1.0f / nLights;
     const bool pow2L = (sc.n_lights & (sc.n_lights - 1)) == 0 && sc.n_lights <= (1 << 24);     // see initial_kernel
     const float Nf = (float)fr.f.numSamplesInReservoir;
-    PixCtx c = make_ctx(sc, fr, g, x, y);
+    PixCtx c = make_ctx<true>(sc, fr, g, x, y);
     uint32_t q[ROMIS_COD_MAX];
-    for (int a = 0; a < K1; a++) q[a] = rm.nb[(size_t)a * rm.plane + p];
+    // per distribution b and sub-reservoir j, once instead of once per sample: 1 / M and wSum - chosenSampleWeight
+    // (render_utils.cpp:250-254)
+    float invM[ROMIS_COD_MAX][CAP], wRest[ROMIS_COD_MAX][CAP];
+    for (int a = 0; a < K1; a++) {
+        q[a] = rm.nb[(size_t)a * rm.plane + p];
+        const int by = (int)(q[a] >> 16), bx = (int)(q[a] & 0xffffu);
+        const size_t bp = (size_t)by * fr.W + bx;
+        ROMIS_FOR_SUB(j, NT, N) {
+            invM[a][j] = 1.0f / (float)res_m(in, by, j)[bx];
+            wRest[a][j] = rm.wsum[(size_t)j * rm.plane + bp] - rm.chosen[(size_t)j * rm.plane + bp];
+        }
+    }
     float Al[PROG ? 3 * ROMIS_COD_MAX : 1];
     v3 fin = V3(0, 0, 0);
     const float invTotalSamples = 1.0f / (float)(int32_t)((uint32_t)K1 * fr.f.numSamplesInReservoir);          // :138,199
@@ -234,51 +256,71 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
             const uint4 rec = res_rec(in, ay, j)[ax];
             light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), spos[j], scol[j]);
         }
+        // The samples shaded at this pixel (:184-186), once: the value is also distribution 0's target pdf (plane 0 of the
+        // neighbour grid is the pixel itself, neighbour_selection.cpp:40,71).
+        v3 shade[CAP];
+        _Pragma("unroll 1") for (int j = 0; j < N; j++) shade[j] = c.miss ? V3(0, 0, 0) : compute_shading(c, es, spos[j], scol[j]);
         float V[CAP][ROMIS_COD_MAX];                                                // colVecW of every sample of pixel a
         for (int b = 0; b < K1; b++) {                                              // :178-181, distribution b at all N samples
             const int by = (int)(q[b] >> 16), bx = (int)(q[b] & 0xffffu);
-            const size_t bp = (size_t)by * fr.W + bx;
-            PixCtx cb = make_ctx(sc, fr, g, bx, by);
+            PixCtx cb;
+            const bool own = b == 0;
+            // distribution a at pixel a's own samples: the target pdf the initial pass stored with the record (res_finish)
+            const bool stored = b == a && sc.n_lights != 0;
+            if (!own && !stored) cb = make_ctx<true>(sc, fr, g, bx, by);
             _Pragma("unroll 1") for (int j = 0; j < N; j++) {      // one copy of the evaluation: the kernel is instruction-cache bound
                 float w = 0.0f;
-                const float pdf = target_pdf(cb, es, spos[j], scol[j]);
+                float pdf;
+                if (own) pdf = c.miss ? 0.0f : length3(shade[j]);
+                else if (stored) pdf = res_pdf(in, by, j)[bx];
+                else pdf = target_pdf(cb, es, spos[j], scol[j]);
                 if (pdf != 0.0f) {                                                  // render_utils.cpp:248-256
                     const float mock = pow2L ? pdf * nLights : pdf / invPdf;
-                    const float Mb = (float)res_m(in, by, j)[bx];
-                    const float arbitraryWeight = (1.0f / pdf) * (1.0f / Mb) *
-                                                  ((rm.wsum[(size_t)j * rm.plane + bp] - rm.chosen[(size_t)j * rm.plane + bp]) + mock);
+                    const float arbitraryWeight = (1.0f / pdf) * invM[b][j] * (wRest[b][j] + mock);
                     w = 1.0f / arbitraryWeight;
                 }
                 V[j][b] = w;
             }
         }
+        v3 sampleColor[CAP]; float scaleFactor[CAP];
         _Pragma("unroll 1") for (int j = 0; j < N; j++) {                           // :173
-            // the sample shaded at this pixel (:184-186); a zero result adds (+-0) to the contribution vectors
-            v3 sampleColor = V3(0, 0, 0);
-            if (!c.miss) {
-                const v3 shading = compute_shading(c, es, spos[j], scol[j]);
-                if (!(shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) && visible(sc, c, spos[j])) sampleColor = shading;
-            }
+            // a zero result adds (+-0) to the contribution vectors: no shadow ray
+            v3 sc_j = V3(0, 0, 0);
+            const v3 shading = shade[j];
+            if (!(shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) && visible(sc, c, spos[j])) sc_j = shading;
+            sampleColor[j] = sc_j;
             if (PROG) {                                                             // :190-200
                 v3 sumAlphaProducts = V3(0, 0, 0); float sumSampleFractionProducts = FLT_MIN;
                 for (int b = 0; b < K1; b++) {
                     sumAlphaProducts = add3(sumAlphaProducts, scale3(V3(Al[0 * K1 + b], Al[1 * K1 + b], Al[2 * K1 + b]), V[j][b]));
                     sumSampleFractionProducts += fractionOfTotalSamples * V[j][b];
                 }
-                fin = add3(fin, scale3(sub3(div3(sampleColor, sumSampleFractionProducts), div3(sumAlphaProducts, sumSampleFractionProducts)), invTotalSamples));
+                fin = add3(fin, scale3(sub3(div3(sc_j, sumSampleFractionProducts), div3(sumAlphaProducts, sumSampleFractionProducts)), invTotalSamples));
             }
-            float scaleFactor = FLT_MIN;                                            // :203-205
-            for (int b = 0; b < K1; b++) scaleFactor += Nf * V[j][b];
-            scaleFactor = 1.0f / scaleFactor;
-            for (int b = 0; b < K1; b++) V[j][b] *= scaleFactor;                    // :208
-            for (int i = 0; i < K1; i++) {
-                const float vi = V[j][i];
-                for (int b = 0; b < K1; b++) rm.tech[(size_t)(i * K1 + b) * rm.plane + p] += vi * V[j][b];      // :209
-                const float scaleColVecConst = scaleFactor * vi;                    // :211
-                rm.contrib[(size_t)(0 * K1 + i) * rm.plane + p] += sampleColor.x * scaleColVecConst;
-                rm.contrib[(size_t)(1 * K1 + i) * rm.plane + p] += sampleColor.y * scaleColVecConst;
-                rm.contrib[(size_t)(2 * K1 + i) * rm.plane + p] += sampleColor.z * scaleColVecConst;
+            float sf = FLT_MIN;                                                     // :203-205
+            for (int b = 0; b < K1; b++) sf += Nf * V[j][b];
+            sf = 1.0f / sf;
+            for (int b = 0; b < K1; b++) V[j][b] *= sf;                             // :208
+            scaleFactor[j] = sf;
+        }
+        // :209-214 for the N samples of pixel a in one pass over the system: every element is read once, takes its N terms
+        // in sample order (the order the reference adds them in) and is written once.  The matrix is a sum of outer products
+        // v v^T: element (b, i) receives the same products in the same order as (i, b), so only the upper triangle is kept;
+        // the solve and the parity read-back mirror it.
+        for (int i = 0; i < K1; i++) {
+            for (int b = i; b < K1; b++) {
+                float t = rm.tech[(size_t)(i * K1 + b) * rm.plane + p];
+                ROMIS_FOR_SUB(j, NT, N) t += V[j][i] * V[j][b];
+                rm.tech[(size_t)(i * K1 + b) * rm.plane + p] = t;
             }
+            float cx = rm.contrib[(size_t)(0 * K1 + i) * rm.plane + p], cy = rm.contrib[(size_t)(1 * K1 + i) * rm.plane + p],
+                  cz = rm.contrib[(size_t)(2 * K1 + i) * rm.plane + p];
+            ROMIS_FOR_SUB(j, NT, N) {
+                const float scaleColVecConst = scaleFactor[j] * V[j][i];            // :211
+                cx += sampleColor[j].x * scaleColVecConst; cy += sampleColor[j].y * scaleColVecConst; cz += sampleColor[j].z * scaleColVecConst;
+            }
+            rm.contrib[(size_t)(0 * K1 + i) * rm.plane + p] = cx; rm.contrib[(size_t)(1 * K1 + i) * rm.plane + p] = cy;
+            rm.contrib[(size_t)(2 * K1 + i) * rm.plane + p] = cz;
         }
     }
     if (PROG) rm.acc[p] = make_float4(fin.x, fin.y, fin.z, 0.0f);
@@ -294,7 +336,8 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
     const int K1 = rm.K1;
     const size_t p = (size_t)y * fr.W + x;
     float A[ROMIS_COD_MAX * ROMIS_COD_MAX], b[ROMIS_COD_MAX], xs[ROMIS_COD_MAX];
-    for (int i = 0; i < K1 * K1; i++) A[i] = rm.tech[(size_t)i * rm.plane + p];
+    for (int i = 0; i < K1; i++)                                                    // upper triangle stored, see the accumulation
+        for (int b = i; b < K1; b++) A[i * K1 + b] = A[b * K1 + i] = rm.tech[(size_t)(i * K1 + b) * rm.plane + p];
     romis_cod cod;
     romis_cod_compute(&cod, A, K1);
     float sum[3];
@@ -318,6 +361,9 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
     rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
 }
 
+void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g) {
+    ctx_kernel<<<grid, block, 0, s>>>(sc, fr, g);
+}
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm) {
     rmis_neighbours_kernel<<<grid, block, 0, s>>>(sc, fr, g, rm);
 }

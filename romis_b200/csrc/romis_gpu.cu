@@ -80,7 +80,7 @@ struct romis_ctx {
     bool exported = false;
 
     // R-MIS (romis_render_frame_rmis): neighbour grid and accumulator of the last frame
-    DevBuf rmis_nb, rmis_acc, romis_wsum, romis_chosen, romis_tech, romis_contrib, romis_alpha;
+    DevBuf rmis_pv, rmis_nb, rmis_acc, romis_wsum, romis_chosen, romis_tech, romis_contrib, romis_alpha;
     int rmis_W = 0, rmis_H = 0, rmis_K1 = 0;
 
     // parity capture
@@ -118,7 +118,7 @@ static ResBuf resbuf(const romis_ctx* c, int i) {
     ResBuf b; b.base = (unsigned char*)c->res[i].p; b.row_stride = c->row_stride; b.W = c->W; b.N = c->N; return b;
 }
 static GBufDev gbuf(const romis_ctx* c) {
-    GBufDev g; g.tn = (float4*)c->gb_tn.p; g.mesh = (uint32_t*)c->gb_mesh.p; g.uv = (float2*)c->gb_uv.p; return g;
+    GBufDev g; g.tn = (float4*)c->gb_tn.p; g.mesh = (uint32_t*)c->gb_mesh.p; g.uv = (float2*)c->gb_uv.p; g.pv = nullptr; return g;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,7 +170,7 @@ extern "C" void romis_destroy(romis_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
-                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib, &c->romis_alpha}) b->release();
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_pv, &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib, &c->romis_alpha}) b->release();
     romis_peer_detach(c);
     c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
@@ -785,6 +785,7 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
 
     const size_t px = (size_t)W * H;
     RCHECK(c, c->rmis_nb.ensure(px * K1 * sizeof(uint32_t)));
+    RCHECK(c, c->rmis_pv.ensure(px * 2 * sizeof(float4)));
     c->rmis_W = W; c->rmis_H = H; c->rmis_K1 = K1;
     RmisDev rm; std::memset(&rm, 0, sizeof rm);
     rm.p = *rp; rm.nb = (uint32_t*)c->rmis_nb.p; rm.K1 = K1; rm.plane = px;
@@ -823,22 +824,24 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     RCHECK(c, mark(c, 0, 0));
     const dim3 grid = grid_for(W, H);
     const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
-    launch_primary(c->stream, grid, kBlock, c->sc, fr, gbuf(c), 0, H);                      // render.cpp:68 / :125
+    GBufDev g = gbuf(c); g.pv = (float4*)c->rmis_pv.p;
+    launch_primary(c->stream, grid, kBlock, c->sc, fr, g, 0, H);                            // render.cpp:68 / :125
+    launch_ctx(c->stream, grid, kBlock, c->sc, fr, g);
     RCHECK(c, mark(c, 1, 0));
-    launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, gbuf(c), rm);                // :69 / :126
+    launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, g, rm);                // :69 / :126
     RCHECK(c, mark(c, 7, 0));
-    c->n_launches += 2;
+    c->n_launches += 3;
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
+        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
-        if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164
             launch_romis_solve(c->stream, grid, kBlock, fr, rm, nullptr, true);
             c->n_launches++;
         }
-        if (mode == 1) launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, work), rm);
+        if (mode == 1) launch_romis_accumulate(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm);
         RCHECK(c, mark(c, 9, (int)it));
         c->n_launches += 2;
         RCHECK(c, cudaGetLastError());
@@ -876,7 +879,8 @@ extern "C" int romis_download_romis_system(romis_ctx* c, float* matrices, float*
     RCHECK(c, cudaMemcpy(t.data(), c->romis_tech.p, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
     RCHECK(c, cudaMemcpy(v.data(), c->romis_contrib.p, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t p = 0; p < px; p++) {
-        if (matrices) for (int i = 0; i < K1 * K1; i++) matrices[p * K1 * K1 + i] = t[(size_t)i * px + p];
+        if (matrices) for (int i = 0; i < K1; i++) for (int b = 0; b < K1; b++)       // the device keeps the upper triangle
+            matrices[p * K1 * K1 + i * K1 + b] = t[(size_t)(std::min(i, b) * K1 + std::max(i, b)) * px + p];
         if (contributions) for (int i = 0; i < 3 * K1; i++) contributions[p * 3 * K1 + i] = v[(size_t)i * px + p];
     }
     return ROMIS_OK;

@@ -7,13 +7,13 @@ namespace romis {
 // ------------------------------------------------------------------------------------------------
 // temporal reuse: same-pixel predecessor, M clamp, biased combine of {current, predecessor}
 // ------------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool ES>        // ES: enableShading known to be on, see spatial_kernel
 __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
-    const bool es = fr.f.enableShading != 0;
+    const bool es = ES || fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
     const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
     constexpr int CAP = SubRes<NT>::CAP;
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
 
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                      const ResBuf& cur, const ResBuf& prev, const ResBuf& out) {
-    ROMIS_DISPATCH_N(N, (temporal_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out)));
+    if (fr.f.enableShading) { ROMIS_DISPATCH_N(N, (temporal_kernel<NT, true><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out))); }
+    else { ROMIS_DISPATCH_N(N, (temporal_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out))); }
 }
 }  // namespace romis

@@ -202,8 +202,9 @@ def mis_pass_bytes(mode: str, N: int, K1: int):
     array once; S = 20 B per sub-reservoir record, G = 20 B per pixel."""
     if mode == "rmis":      # gather: own G, K1 grid entries, K1*N neighbour records, accumulator read + write
         return 20 + 4 * K1 + 20 * K1 * N + 24
-    # accumulate: own G, grid, K1*N records + their wSum/chosen, the K1 distributions' G, technique matrix and 3 vectors RMW
-    return 20 + 4 * K1 + (20 + 8) * K1 * N + 20 * K1 + 8 * (K1 * K1 + 3 * K1)
+    # accumulate: own G, grid, K1*N records + their wSum/chosen, the K1 distributions' G, the symmetric technique matrix
+    # (K1 (K1 + 1) / 2 independent elements) and the 3 contribution vectors read + written
+    return 20 + 4 * K1 + (20 + 8) * K1 * N + 20 * K1 + 8 * (K1 * (K1 + 1) // 2 + 3 * K1)
 
 
 def run_mis(args, mode, rank, world):

@@ -400,15 +400,18 @@ static int capture_stage(romis_ctx* c, int pass_id, int buf) {
     return ROMIS_OK;
 }
 
-// Block shape of the pass kernels (launch bounds are for 256 threads; smaller blocks only shorten the tail of short
-// kernels, e.g. thin row bands).  ROMIS_BLOCK_Y=<n> in the environment overrides it for tuning runs.
-static dim3 make_block() {
-    int by = 8;
-    if (const char* e = std::getenv("ROMIS_BLOCK_Y")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) by = v; }
+// Block shapes of the pass kernels (launch bounds are for 256 threads).  The kernels that gather a +-r window (spatial pass, R-MIS /
+// R-OMIS) run 32x8 blocks, the per-pixel streaming ones (primary, initial, temporal, shade) 32x4: measured on B200 at C2, initial
+// 0.995 -> 0.976 ms and shade 0.274 -> 0.266 ms with the smaller block (finer refill of an SM whose warps run for > 100 us), the
+// spatial pass 0.381 -> 0.389 ms (less overlap between the windows of a block).  ROMIS_BLOCK_Y / ROMIS_BLOCK_YS=<n> in the
+// environment override them for tuning runs.
+static dim3 make_block(const char* env, int by) {
+    if (const char* e = std::getenv(env)) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) by = v; }
     return dim3(32, by);
 }
-static const dim3 kBlock = make_block();
-static dim3 grid_for(int W, int rows) { return dim3((W + kBlock.x - 1) / kBlock.x, (rows + kBlock.y - 1) / kBlock.y); }
+static const dim3 kBlock = make_block("ROMIS_BLOCK_Y", 8);
+static const dim3 kBlockS = make_block("ROMIS_BLOCK_YS", 4);
+static dim3 grid_for(int W, int rows, const dim3& b = kBlock) { return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y); }
 
 // (Re)allocates the per-frame buffers for (W, H, N, band, halo).  A change of resolution, band or N drops the temporal
 // history (the reference would read out of bounds).
@@ -470,16 +473,16 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     // work buffers: the two that are not the history
     const int w0 = (c->hist + 1) % 3;
     c->spare = (c->hist + 2) % 3;
-    const dim3 gOwn = grid_for(W, c->y1 - c->y0);
+    const dim3 gOwn = grid_for(W, c->y1 - c->y0, kBlockS);
 
     // 1. primary rays for band + halo rows (the halo G-buffer is re-traced locally instead of exchanged)
-    launch_primary(c->stream, grid_for(W, pey1 - pey0), kBlock, c->sc, fr, gbuf(c), pey0, pey1);
+    launch_primary(c->stream, grid_for(W, pey1 - pey0, kBlockS), kBlockS, c->sc, fr, gbuf(c), pey0, pey1);
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 1, 0));
 
     // 2. initial RIS (+ visibility reuse)
-    launch_initial(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
+    launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 2, 0));
@@ -487,7 +490,7 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
 
     // 3. temporal reuse (in place on w0; reads the history)
     if (f->temporalReuse && c->history_valid) {
-        launch_temporal(c->stream, gOwn, kBlock, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0));
+        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0));
         c->n_launches++;
         RCHECK(c, cudaGetLastError());
         RCHECK(c, mark(c, 3, 0));
@@ -557,7 +560,7 @@ extern "C" int romis_row_hit_counts(romis_ctx* c, const romis_camera* cam, int W
     fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
     fr.W = W; fr.H = H; fr.y0 = 0; fr.y1 = H; fr.ey0 = 0; fr.ey1 = H;
     GBufDev g; g.tn = (float4*)tn.p; g.mesh = (uint32_t*)mesh.p; g.uv = (float2*)uv.p;
-    launch_primary(c->stream, grid_for(W, H), kBlock, c->sc, fr, g, 0, H);
+    launch_primary(c->stream, grid_for(W, H, kBlockS), kBlockS, c->sc, fr, g, 0, H);
     launch_row_hits(c->stream, g, W, H, c->sc.n_meshes, (uint32_t*)rows.p);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(hits_per_row, rows.p, (size_t)H * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
@@ -694,7 +697,7 @@ extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
     for (int k = 0; k < chunks; k++) {
         const int a = c->y0 + (int)((long long)rows * k / chunks), b = c->y0 + (int)((long long)rows * (k + 1) / chunks);
         FrameDev fr = c->fr; fr.y0 = a; fr.y1 = b;
-        launch_shade(c->stream, grid_for(c->W, b - a), kBlock, c->N, c->sc, fr, gbuf(c), resbuf(c, c->cur), (float*)c->rgb.p);
+        launch_shade(c->stream, grid_for(c->W, b - a, kBlockS), kBlockS, c->N, c->sc, fr, gbuf(c), resbuf(c, c->cur), (float*)c->rgb.p);
         c->n_launches++;
         RCHECK(c, cudaGetLastError());
         if (out_rgb) {
@@ -825,8 +828,9 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     const dim3 grid = grid_for(W, H);
     const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
     GBufDev g = gbuf(c); g.pv = (float4*)c->rmis_pv.p;
-    launch_primary(c->stream, grid, kBlock, c->sc, fr, g, 0, H);                            // render.cpp:68 / :125
-    launch_ctx(c->stream, grid, kBlock, c->sc, fr, g);
+    const dim3 gridS = grid_for(W, H, kBlockS);
+    launch_primary(c->stream, gridS, kBlockS, c->sc, fr, g, 0, H);                          // render.cpp:68 / :125
+    launch_ctx(c->stream, gridS, kBlockS, c->sc, fr, g);
     RCHECK(c, mark(c, 1, 0));
     launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, g, rm);                // :69 / :126
     RCHECK(c, mark(c, 7, 0));
@@ -834,7 +838,7 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
+        launch_initial(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164

@@ -840,7 +840,7 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
         fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
         launch_initial(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
-        if (mode == 0) launch_rmis_gather(c->stream, grid, kBlock, c->N, c->sc, fr, g, resbuf(c, work), rm);
+        if (mode == 0) launch_rmis_gather(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164
             launch_romis_solve(c->stream, grid, kBlock, fr, rm, nullptr, true);
             c->n_launches++;

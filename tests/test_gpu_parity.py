@@ -83,6 +83,12 @@ def test_tracer_matches_oracle_bruteforce(renderer, oracle_factory):
         d = d.astype(np.float32)
         d[:50, 0] = 0.0                                   # axis-parallel rays: 1/0 in the slab test
         d[50:100, 1] = 0.0
+        d[100:130, 2] = np.float32(1e-35) * np.where(rng.random(30) < 0.5, -1, 1)   # below the slab test's 2^-100 threshold
+        d[130:160, 0] = np.float32(-1e-42)                # subnormal: 1/d overflows
+        d[160:180, 1] = np.float32(-0.0)
+        d[180:200, 2] = np.float32(2.0 ** -99)            # just above the threshold: 1/d = 2^99
+        o[200:230, 0] = verts[rng.integers(0, len(verts), 30), 0]       # origins exactly on a vertex plane, axis-parallel
+        d[200:230, 0] = 0.0
         tfar = np.where(rng.random(n) < 0.5, np.float32(3.4e38), rng.uniform(0.1, 5.0, n)).astype(np.float32)
         gh, gt, gu, gv, gtri = renderer.trace_rays(o, d, tfar, any_hit=False)
         oh, ot, ou, ov, otri = orc.trace_rays(o, d, tfar, any_hit=False)

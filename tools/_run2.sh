@@ -1,4 +1,2 @@
-python tools/quick_bench.py 2>&1 | tail -1
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py tests/test_gpu_romis.py tests/test_gpu_rmis.py -m gpu -x -q 2>&1 | tail -2
-python bench.py --config romis --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('romis', d['ms_per_step'], d['roofline']['stages_ms_per_frame'])"
+for by in 4 8; do for c in romis rmis; do ROMIS_BLOCK_Y=$by python bench.py --config $c --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('BY=$by $c', round(d['ms_per_step'],3), d['roofline']['stages_ms_per_frame'])"; done; done

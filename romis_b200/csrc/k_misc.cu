@@ -57,12 +57,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev s
         color = add3(color, scol);
     }
     color = div3(color, (float)N);                                                  // :63
-    if (fr.f.enableToneMapping) {                                                   // tone_mapping.cpp:8-11
-        float ig = 1.0f / fr.f.gamma;
-        color = V3(romis_powf(1.0f - romis_expf(fr.f.exposure * -color.x), ig),
-                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.y), ig),
-                   romis_powf(1.0f - romis_expf(fr.f.exposure * -color.z), ig));
-    }
+    if (fr.f.enableToneMapping) color = tone_map(color, fr.f);                      // tone_mapping.cpp:8-11
     size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;                                   // screen.cpp:37-43
     rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
 }

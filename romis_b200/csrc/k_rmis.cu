@@ -262,16 +262,21 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
             const bool own = b == 0;
             // distribution a at pixel a's own samples: the target pdf the initial pass stored with the record (res_finish)
             const bool stored = b == a && sc.n_lights != 0;
+            float im[CAP], wr[CAP];                                 // requested before the context so that the latencies overlap
+            ROMIS_FOR_SUB(j, NT, N) { im[j] = invM[b][j]; wr[j] = wRest[b][j]; }
             if (!own && !stored) cb = make_ctx<true>(sc, fr, g, bx, by);
             _Pragma("unroll 1") for (int j = 0; j < N; j++) {      // one copy of the evaluation: the kernel is instruction-cache bound
                 float w = 0.0f;
+                float imj = im[0], wrj = wr[0];
+                if (NT > 0) { ROMIS_FOR_SUB(jj, NT, N) { if (jj == j) { imj = im[jj]; wrj = wr[jj]; } } }
+                else { imj = im[j]; wrj = wr[j]; }
                 float pdf;
                 if (own) pdf = c.miss ? 0.0f : length3(shade[j]);
                 else if (stored) pdf = res_pdf(in, by, j)[bx];
                 else pdf = target_pdf(cb, es, spos[j], scol[j]);
                 if (pdf != 0.0f) {                                                  // render_utils.cpp:248-256
                     const float mock = pow2L ? pdf * nLights : pdf / invPdf;
-                    const float arbitraryWeight = (1.0f / pdf) * invM[b][j] * (wRest[b][j] + mock);
+                    const float arbitraryWeight = (1.0f / pdf) * imj * (wrj + mock);
                     w = 1.0f / arbitraryWeight;
                 }
                 V[j][b] = w;

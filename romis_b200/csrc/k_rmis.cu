@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
     const size_t p = (size_t)y * fr.W + x;
-    PixCtx c = make_ctx(sc, fr, g, x, y);
+    PixCtx c = make_ctx<true>(sc, fr, g, x, y);
     // A miss pixel shades every sample to exactly +0 (see target_pdf) and the balance weight is 0 / (FLT_MIN + ...) = 0:
     // the iteration adds +0 to the accumulator, which leaves it unchanged.
     if (c.miss) return;
@@ -159,6 +159,9 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
     v3 finalColor = V3(0, 0, 0);
     for (int a = 0; a < n; a++) {
         const int qy = (int)(q[a] >> 16), qx = (int)(q[a] & 0xffffu);
+        // The pixel's own reservoir under initialSamplesVisibilityCheck: the initial pass shot this very ray (same hit point, same
+        // sample) and zeroed W when it was blocked (light.cpp:86-87), so W != 0 below says "visible" without a second ray.
+        const bool own_checked = fr.f.initialSamplesVisibilityCheck != 0 && q[a] == q[0];
         _Pragma("unroll 1") for (int j = 0; j < N; j++) {
             const uint4 rec = res_rec(in, qy, j)[qx];
             const float Wj = __uint_as_float(rec.w);
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(Scene
                 }
                 misWeight = numerator / denominator;
             }
-            v3 sampleColor = visible(sc, c, pos) ? shading : V3(0, 0, 0);           // render.cpp:103-105
+            v3 sampleColor = (own_checked || visible(sc, c, pos)) ? shading : V3(0, 0, 0);  // render.cpp:103-105
             finalColor = add3(finalColor, div3(scale3(scale3(sampleColor, misWeight), Wj), (float)N));      // :106
         }
     }
@@ -284,7 +287,8 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
         }
         v3 sampleColor[CAP]; float scaleFactor[CAP];
         _Pragma("unroll 1") for (int j = 0; j < N; j++) {                           // :173
-            // a zero result adds (+-0) to the contribution vectors: no shadow ray
+            // a zero result adds (+-0) to the contribution vectors: no shadow ray.  (Reusing the initial pass's verdict for the
+            // pixel's own samples, as the R-MIS gather does, costs this kernel more in registers than the two rays: 22.0 -> 22.5 ms.)
             v3 sc_j = V3(0, 0, 0);
             const v3 shading = shade[j];
             if (!(shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) && visible(sc, c, spos[j])) sc_j = shading;

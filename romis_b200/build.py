@@ -29,8 +29,6 @@ if os.environ.get("ROMIS_DEFS"):       # tuning knob: extra -D flags, space sepa
     FLAGS += ["-D" + d for d in os.environ["ROMIS_DEFS"].split()]
 if os.environ.get("ROMIS_LIB_OUT"):    # tuning builds go next to the objects, the product stays libromis_gpu.so
     LIB = os.environ["ROMIS_LIB_OUT"]
-if os.environ.get("ROMIS_MINB"):       # tuning knob, see device_common.cuh
-    FLAGS.append("-DROMIS_MINB=" + os.environ["ROMIS_MINB"])
 
 
 def _deps():

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) ctx_kernel(SceneDev sc, FrameDev fr, GBuf
 // One iteration's gather (render.cpp:79-112): every pixel shades the samples of its neighbourhood pixels at ITS OWN hit
 // point, each weighted by the MIS weight and the sample's outputWeight, with a shadow ray per sample.
 template <int NT>
-__global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) rmis_gather_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_GATHER) rmis_gather_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
     int x, y; thread_pixel<false>(x, y);
     if (x >= fr.W || y >= fr.H) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;

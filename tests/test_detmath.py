@@ -93,3 +93,33 @@ def test_specular_cutoff_claim():
         assert np.float32(orc.orc_powf(ctypes.c_float(float(c) * 1.002), ctypes.c_float(s))) != 0.0
     for s in (0.0, -2.0, 0.5, float("nan"), float("inf")):
         assert lib.romis_specular_cutoff(ctypes.c_float(s)) == 0.0
+
+
+def test_pow_with_exponent_one_is_the_identity():
+    """The tone-mapping shortcut of the kernels (tone_map, csrc/device_common.cuh) skips pow(x, 1 / gamma) for gamma = 1:
+    romis_powf(x, 1) must return x bit for bit, for every kind of x."""
+    orc = Oracle()
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([
+        rng.uniform(0, 1, 20000).astype(np.float32),                       # the range 1 - exp(-exposure * c) lives in
+        rng.uniform(-4, 4, 5000).astype(np.float32),
+        rng.integers(0, 1 << 32, 20000, dtype=np.uint64).astype(np.uint32).view(np.float32),    # any bit pattern
+        np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, -1e-45, 1.17549435e-38, 3.4028235e38, 5.9e-39], np.float32)])
+    for x in xs:
+        r = np.float32(orc.lib.orc_powf(float(x), 1.0))
+        if np.isnan(x):
+            assert np.isnan(r)
+        else:
+            assert r.view(np.uint32) == x.view(np.uint32), f"pow({x!r}, 1) = {r!r}"
+    orc.close()
+
+
+def test_uniform_float_conversion_is_one_multiplication():
+    """Device form of romis_rand_to_unit: float(r) * 2^-31 has the bits of ((float(r) - 0) / (2^31 - 0)) * (1 - 0) + 0 for r >= 0."""
+    rng = np.random.default_rng(12)
+    r = np.concatenate([rng.integers(0, 1 << 31, 200000, dtype=np.int64), np.array([0, 1, 2, (1 << 31) - 1, (1 << 31) - 64, (1 << 24) + 1])])
+    f = r.astype(np.float32)                                               # int -> float, round to nearest even, as the cast
+    host = (((f - np.float32(0)) / (np.float32(2147483648.0) - np.float32(0))) * (np.float32(1) - np.float32(0))) + np.float32(0)
+    dev = f * np.float32(4.656612873077392578125e-10)
+    assert np.array_equal(host.view(np.uint32), dev.view(np.uint32))
+    assert host.min() >= 0 and host.max() <= 1 and not np.signbit(host).any()

@@ -23,13 +23,16 @@ template <int NT> struct SubRes {
     float chosen[CAP];  // chosenSampleWeights (reservoir.cpp:27): only R-OMIS reads it, dead code in every other kernel
     float pdf[CAP];     // target pdf of the held sample at THIS pixel, as evaluated when it was accepted (see res_finish)
     uint32_t M[CAP];
-    uint64_t cnt[CAP];
+    uint32_t cnt[CAP];  // routed sums of the sources' M, saturating at 2^32-1 (= the clamp of the exact sum: res_take_counts)
 };
+
+// min(a + b, 2^32 - 1): a chain of these equals the exact (size_t) sum clamped once at the end, one register instead of two
+__device__ __forceinline__ uint32_t sat_add_u32(uint32_t a, uint32_t b) { const uint32_t s = a + b; return s < a ? 0xffffffffu : s; }
 
 // Reservoir::Reservoir (reservoir.h:29-32)
 template <int NT> __device__ __forceinline__ void res_init(SubRes<NT>& r, int N) {
     ROMIS_FOR_SUB(j, NT, N) {
-        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0ull; r.pdf[j] = 0.0f; r.chosen[j] = 0.0f;
+        r.light[j] = ROMIS_NO_LIGHT; r.u[j] = 0.0f; r.v[j] = 0.0f; r.W[j] = 0.0f; r.wSum[j] = FLT_MIN; r.M[j] = 1u; r.cnt[j] = 0u; r.pdf[j] = 0.0f; r.chosen[j] = 0.0f;
     }
 }
 
@@ -109,13 +112,13 @@ template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, i
     if (own_pdf >= 0.0f && rec.x != ROMIS_NO_LIGHT) pdf = own_pdf;
     else { v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col); pdf = target_pdf(c, es, pos, col); }
     int idx = res_update(r, N, rec.x, u, v, pdf, pdf * Wi * (float)Mi, rk, rc);
-    if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] += (uint64_t)Mi; } }
-    else r.cnt[idx] += (uint64_t)Mi;
+    if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] = sat_add_u32(r.cnt[j], Mi); } }
+    else r.cnt[idx] = sat_add_u32(r.cnt[idx], Mi);
 }
 
 // sampleNums = routed sums of the sources' M (reservoir.cpp:54,82); saturates at 2^32-1
 template <int NT> __device__ __forceinline__ void res_take_counts(SubRes<NT>& r, int N) {
-    ROMIS_FOR_SUB(j, NT, N) r.M[j] = r.cnt[j] > 0xffffffffull ? 0xffffffffu : (uint32_t)r.cnt[j];
+    ROMIS_FOR_SUB(j, NT, N) r.M[j] = r.cnt[j];
 }
 
 }  // namespace romis

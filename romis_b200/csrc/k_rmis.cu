@@ -64,7 +64,12 @@ __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32
                 if (in_pairs) {
                     const uint32_t b1 = unsampled - 1u;
                     const uint32_t xx = lemire32(ek, ec, unsampled * b1);
-                    const uint32_t p0 = xx / b1; p1 = xx % b1; have_p1 = true;
+                    // xx / b1 and xx % b1: xx < unsampled * b1 <= 3721 * 3720 < 2^24 (r <= ROMIS_RMIS_MAX_R), so both operands are
+                    // exact floats, the quotient is below 3721 and the approximate division is off by less than one: one fix-up step
+                    uint32_t p0 = (uint32_t)__fdividef((float)xx, (float)b1);
+                    int32_t rem = (int32_t)(xx - p0 * b1);
+                    if (rem < 0) { p0--; rem += (int32_t)b1; } else if (rem >= (int32_t)b1) { p0++; rem -= (int32_t)b1; }
+                    p1 = (uint32_t)rem; have_p1 = true;
                     --unsampled; take = p0 < n;
                 } else { --unsampled; take = lemire32(ek, ec, unsampled + 1u) < n; }
             }

@@ -456,6 +456,9 @@ def main():
                        "sharding": (f"{world} row bands, halo = radius rows, " + ("pushed into peer-mapped (CUDA IPC) buffers over NVLink, flag-ordered" if br.transport == "peer" else "NCCL p2p" + (f" (peer mapping unavailable: {br.fallback_reason})" if br.fallback_reason else ""))) if world > 1 else "single GPU",
                        "band_edges": br.edges if br.edges is not None else "equal rows"},
             "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
+            # the same count against the initial RIS pass alone (rank 0's band when the frame is sharded)
+            "gcandidates_per_s_initial_pass": (round(px * feat.initialLightSamples / (per_pass["initial"]["ms_per_launch"] * 1e-3) / 1e9, 2)
+                                               if world == 1 and per_pass.get("initial", {}).get("ms_per_launch") else None),
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(6 * 16 * len(scene.lights) + 256),
                     "d2h_bytes_per_step": int(px * 12), "gcandidates_per_s": W * H * feat.initialLightSamples * e2e_fps / 1e9},

@@ -21,7 +21,7 @@ sass = [0, 0, 0]
 cur_file = ""
 for r in rows[hi + 1:]:
     if len(r) < len(h):
-        if r and r[0] == "File Name": cur_file = r[1].split("/")[-1]
+        if r and r[0] in ("File Name", "File Path"): cur_file = r[1].split("/")[-1]
         continue
     try:
         inst, smp, thr = int(r[iI] or 0), int(r[iN] or 0), int(r[iT] or 0)

@@ -28,7 +28,7 @@ agg = collections.OrderedDict()
 cur_file = ""
 for r in rows[hi[0] + 1:]:          # one block per source file and captured launch: summed
     if len(r) < len(h) or not r[0] or r[0] == "Line No":
-        if r and r[0] == "File Name": cur_file = r[1].split("/")[-1]
+        if r and r[0] in ("File Name", "File Path"): cur_file = r[1].split("/")[-1]
         continue
     a = agg.setdefault((r[0], cur_file[:18] + ": " + r[1].strip()[:100]), [0, 0, 0])
     a[0] += num(r[iR]); a[1] += num(r[iS]); a[2] += num(r[iI])

@@ -143,9 +143,27 @@ int romis_abi_version(void);
 int romis_upload_scene(romis_ctx* ctx, const romis_mesh_desc* meshes, int n_meshes,
                        const romis_texture* textures, int n_textures);
 /* Uploads scene.lights.  The reference reads them fresh every frame (light.cpp:46-66) and the UI edits them without
- * notification, so call this every frame: an unchanged table is detected and costs no transfer.  Fewer lights than before
- * drop the temporal history (it stores light indices). */
+ * notification (ui.cpp:172-261), so call this every frame: every light is compared with what the device holds and only the
+ * changed ones are sent (an unchanged table costs one pass over the caller's array and no transfer).
+ * Edits and the temporal history: the reference's reservoirs hold LightSample{position, color} by value (reservoir.h:18-26), so
+ * a history sample keeps the position / colour its light had when it was drawn, whatever happens to the light afterwards
+ * (render_utils.cpp:154-170).  This call preserves exactly that: the old record of an edited or removed light is archived on
+ * the device and the history samples drawn from it keep evaluating against the archived record.  Adding, removing, moving or
+ * recolouring lights therefore never resets the history. */
 int romis_upload_lights(romis_ctx* ctx, const romis_light* lights, int n_lights);
+/* Same, for callers that know what they edited (the UI's light controls edit one selected light, ui.cpp:172-261): only
+ * lights [first_dirty, first_dirty + n_dirty) are examined, everything else is taken as unchanged -- O(n_dirty) host work
+ * instead of O(n_lights).  n_dirty == 0 is a no-op.  If n_lights differs from the current table the whole table is examined. */
+int romis_upload_lights_range(romis_ctx* ctx, const romis_light* lights, int n_lights, int first_dirty, int n_dirty);
+/* Archive bookkeeping (only needed with several contexts rendering bands of ONE frame: halo rows carry archive slots from band
+ * to band, so every context must recycle the same slots at the same time).  With `auto` on (default) a context recycles the
+ * slots its own history no longer holds at the next edit.  Hosts of banded contexts switch it off and, before every light
+ * upload: fetch every context's marks (1 = slot still held by its history; n_slots = 0 when no edit is pending), OR them
+ * across the contexts and hand the result to romis_light_archive_release on every context. */
+int romis_set_light_archive_auto(romis_ctx* ctx, int on);
+int romis_light_archive_marks(romis_ctx* ctx, uint8_t* marks, int capacity, int* n_slots);
+int romis_light_archive_release(romis_ctx* ctx, const uint8_t* keep, int n_slots);
+int romis_light_archive_size(romis_ctx* ctx, int* n_slots, int* n_held);
 
 /* ---- the frame ---- */
 /* One ReSTIR frame = renderReSTIR (render.cpp:28-62): primary hits -> initial RIS (+ visibility
@@ -294,6 +312,10 @@ int romis_last_frame_timings(romis_ctx* ctx, romis_timings* out);
 /* ---- pinned host memory for out_rgb (Screen::pixels() storage) ---- */
 void* romis_host_alloc(size_t bytes);
 void romis_host_free(void* p);
+/* Page-lock / release memory the caller owns (e.g. the std::vector behind Screen::pixels(), screen.h): out_rgb copies into
+ * registered memory run as asynchronous DMA overlapped with shading, pageable memory goes through the driver's staging. */
+int romis_host_register(void* p, size_t bytes);
+int romis_host_unregister(void* p);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@
 #include <utils/common.h>
 #include <framework/trackball.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -37,10 +38,21 @@ namespace {
 struct GpuState {
     romis_ctx* ctx = nullptr;
     const void* sceneKey = nullptr;     // identity of the uploaded geometry
-    size_t sceneSig = 0;
+    uint64_t sceneSig = 0;
+    bool sceneDirty = true;             // romis_dropin_invalidate_scene (hook next to EmbreeInterface::changeScene)
     uint64_t seed = 0x524f4d4953ull;    // "ROMIS"
     uint32_t frame = 0;
-    ~GpuState() { if (ctx) romis_destroy(ctx); }
+    // lights: a persistent POD copy of scene.lights; with the UI hook (romis_dropin_lights_dirty) only the marked range is
+    // converted and examined, without it the whole table is converted and compared every frame
+    std::vector<romis_light> lights;
+    bool lightsHooked = false, lightsAllDirty = true;
+    int dirtyFirst = 0, dirtyEnd = 0;
+    // Screen::pixels() storage registered as page-locked memory, so the read-back is an asynchronous DMA into it
+    void* pinnedPtr = nullptr; size_t pinnedBytes = 0;
+    ~GpuState() {
+        if (pinnedPtr) romis_host_unregister(pinnedPtr);
+        if (ctx) romis_destroy(ctx);
+    }
 };
 // one context per calling thread: the reference's CLI mode renders one camera per std::thread (main.cpp:213-230)
 thread_local GpuState g;
@@ -49,11 +61,28 @@ void check(int rc, const char* what) {
     if (rc != ROMIS_OK) throw std::runtime_error(std::string(what) + ": " + romis_last_error(g.ctx));   // render.cpp:278 throws too
 }
 
-size_t geometrySignature(const Scene& scene) {
-    size_t h = scene.meshes.size();
+// FNV-1a over everything romis_upload_scene consumes: vertices, indices, materials, texture identity and size.  One pass over
+// the geometry per frame (a few hundred KB for the reference's scenes) against a frame of rendering; a maintainer who hooks
+// romis_dropin_invalidate_scene next to EmbreeInterface::changeScene (embree_interface.cpp:53-56) can drop it.
+uint64_t fnv(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+uint64_t geometrySignature(const Scene& scene) {
+    uint64_t h = 1469598103934665603ull;
+    const size_t nm = scene.meshes.size();
+    h = fnv(h, &nm, sizeof nm);
     for (const Mesh& m : scene.meshes) {
-        h = h * 1000003u + m.vertices.size(); h = h * 1000003u + m.triangles.size();
-        if (!m.vertices.empty()) { uint32_t b; std::memcpy(&b, &m.vertices[0].position.x, 4); h = h * 1000003u + b; }
+        const size_t nv = m.vertices.size(), nt = m.triangles.size();
+        h = fnv(h, &nv, sizeof nv); h = fnv(h, &nt, sizeof nt);
+        if (nv) h = fnv(h, m.vertices.data(), nv * sizeof(Vertex));
+        if (nt) h = fnv(h, m.triangles.data(), nt * sizeof(glm::uvec3));
+        h = fnv(h, &m.material.kd.x, 12); h = fnv(h, &m.material.ks.x, 12);
+        h = fnv(h, &m.material.shininess, 4); h = fnv(h, &m.material.transparency, 4);
+        const Image* img = m.material.kdTexture.get();
+        h = fnv(h, &img, sizeof img);
+        if (img) { h = fnv(h, &img->width, sizeof img->width); h = fnv(h, &img->height, sizeof img->height); }
     }
     return h;
 }
@@ -90,27 +119,54 @@ void uploadScene(const Scene& scene) {
     check(romis_upload_scene(g.ctx, descs.data(), (int)descs.size(), textures.data(), (int)textures.size()), "romis_upload_scene");
 }
 
-void uploadLights(const Scene& scene) {     // scene.lights is read fresh every frame by the reference (light.cpp:46-66)
-    std::vector<romis_light> lights(scene.lights.size());
-    for (size_t i = 0; i < scene.lights.size(); i++) {
-        romis_light l; std::memset(&l, 0, sizeof l);
-        const auto& v = scene.lights[i];
-        if (std::holds_alternative<PointLight>(v)) {
-            const PointLight& p = std::get<PointLight>(v); l.type = ROMIS_LIGHT_POINT;
-            std::memcpy(l.p0, &p.position.x, 12); std::memcpy(l.c0, &p.color.x, 12);
-        } else if (std::holds_alternative<SegmentLight>(v)) {
-            const SegmentLight& s = std::get<SegmentLight>(v); l.type = ROMIS_LIGHT_SEGMENT;
-            std::memcpy(l.p0, &s.endpoint0.x, 12); std::memcpy(l.e1, &s.endpoint1.x, 12);
-            std::memcpy(l.c0, &s.color0.x, 12); std::memcpy(l.c1, &s.color1.x, 12);
-        } else {
-            const ParallelogramLight& p = std::get<ParallelogramLight>(v); l.type = ROMIS_LIGHT_PARALLELOGRAM;
-            std::memcpy(l.p0, &p.v0.x, 12); std::memcpy(l.e1, &p.edge01.x, 12); std::memcpy(l.e2, &p.edge02.x, 12);
-            std::memcpy(l.c0, &p.color0.x, 12); std::memcpy(l.c1, &p.color1.x, 12);
-            std::memcpy(l.c2, &p.color2.x, 12); std::memcpy(l.c3, &p.color3.x, 12);
-        }
-        lights[i] = l;
+romis_light toPod(const std::variant<PointLight, SegmentLight, ParallelogramLight>& v) {
+    romis_light l; std::memset(&l, 0, sizeof l);
+    if (std::holds_alternative<PointLight>(v)) {
+        const PointLight& p = std::get<PointLight>(v); l.type = ROMIS_LIGHT_POINT;
+        std::memcpy(l.p0, &p.position.x, 12); std::memcpy(l.c0, &p.color.x, 12);
+    } else if (std::holds_alternative<SegmentLight>(v)) {
+        const SegmentLight& s = std::get<SegmentLight>(v); l.type = ROMIS_LIGHT_SEGMENT;
+        std::memcpy(l.p0, &s.endpoint0.x, 12); std::memcpy(l.e1, &s.endpoint1.x, 12);
+        std::memcpy(l.c0, &s.color0.x, 12); std::memcpy(l.c1, &s.color1.x, 12);
+    } else {
+        const ParallelogramLight& p = std::get<ParallelogramLight>(v); l.type = ROMIS_LIGHT_PARALLELOGRAM;
+        std::memcpy(l.p0, &p.v0.x, 12); std::memcpy(l.e1, &p.edge01.x, 12); std::memcpy(l.e2, &p.edge02.x, 12);
+        std::memcpy(l.c0, &p.color0.x, 12); std::memcpy(l.c1, &p.color1.x, 12);
+        std::memcpy(l.c2, &p.color2.x, 12); std::memcpy(l.c3, &p.color3.x, 12);
     }
-    check(romis_upload_lights(g.ctx, lights.data(), (int)lights.size()), "romis_upload_lights");
+    return l;
+}
+
+// scene.lights is read fresh every frame by the reference (light.cpp:46-66) and edited by the UI without notification
+// (ui.cpp:172-261).  Unhooked: convert and hand over the whole table, romis_upload_lights finds what changed.  Hooked (the UI
+// calls romis_dropin_lights_dirty after an edit): only the marked lights are converted and examined, an untouched table costs
+// nothing.  Either way the history keeps its samples as drawn (romis_gpu.h, romis_upload_lights).
+void uploadLights(const Scene& scene) {
+    const size_t n = scene.lights.size();
+    const bool all = !g.lightsHooked || g.lightsAllDirty || g.lights.size() != n;
+    if (all) {
+        g.lights.resize(n);
+        for (size_t i = 0; i < n; i++) g.lights[i] = toPod(scene.lights[i]);
+        check(romis_upload_lights(g.ctx, g.lights.data(), (int)n), "romis_upload_lights");
+    } else if (g.dirtyEnd > g.dirtyFirst) {
+        const int a = std::max(0, g.dirtyFirst), b = std::min((int)n, g.dirtyEnd);
+        for (int i = a; i < b; i++) g.lights[i] = toPod(scene.lights[i]);
+        check(romis_upload_lights_range(g.ctx, g.lights.data(), (int)n, a, std::max(0, b - a)), "romis_upload_lights_range");
+    }
+    g.lightsAllDirty = false; g.dirtyFirst = g.dirtyEnd = 0;
+}
+
+// Screen::pixels() is a std::vector<glm::vec3> (pageable): registered once as page-locked memory, the device-to-host copy of
+// the image becomes an asynchronous DMA that overlaps the shading of the next rows (romis_frame_end)
+float* screenStorage(Screen& screen) {
+    std::vector<glm::vec3>& px = screen.pixels();
+    void* p = px.data(); const size_t bytes = px.size() * sizeof(glm::vec3);
+    if (p != g.pinnedPtr || bytes != g.pinnedBytes) {
+        if (g.pinnedPtr) romis_host_unregister(g.pinnedPtr);
+        g.pinnedPtr = nullptr; g.pinnedBytes = 0;
+        if (romis_host_register(p, bytes) == ROMIS_OK) { g.pinnedPtr = p; g.pinnedBytes = bytes; }     // failure: pageable still works
+    }
+    return &px[0].x;
 }
 
 romis_features toPod(const Features& f) {
@@ -131,6 +187,17 @@ romis_features toPod(const Features& f) {
 // Random stream of the next frame (parity runs pin it; the interactive renderer can leave the defaults).
 extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame) { g.seed = seed; g.frame = frame; }
 
+// Optional hooks for the maintainer.  romis_dropin_invalidate_scene: next to EmbreeInterface::changeScene (ui.cpp:104-106).
+// romis_dropin_lights_dirty: after the UI edited lights [first, first + count) (ui.cpp:172-261; count < 0 = all of them,
+// e.g. after adding / removing one); once called, frames no longer compare the whole table.
+extern "C" void romis_dropin_invalidate_scene(void) { g.sceneDirty = true; }
+extern "C" void romis_dropin_lights_dirty(int first, int count) {
+    g.lightsHooked = true;
+    if (count < 0) { g.lightsAllDirty = true; return; }
+    if (g.dirtyEnd <= g.dirtyFirst) { g.dirtyFirst = first; g.dirtyEnd = first + count; }
+    else { g.dirtyFirst = std::min(g.dirtyFirst, first); g.dirtyEnd = std::max(g.dirtyEnd, first + count); }
+}
+
 // half extents of the image plane: Trackball keeps them private (trackball.h:55-56).  The maintainer either adds two
 // accessors or, as here, the caller provides them; they are tan(fovy/2) and aspect*tan(fovy/2) (trackball.cpp:26-27).
 static thread_local float g_halfW = 0.0f, g_halfH = 0.0f;
@@ -143,8 +210,10 @@ static romis_camera prepare(const Scene& scene, const Trackball& camera) {
         if (romis_create(&dev, 1, &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
     }
     // EmbreeInterface::changeScene (embree_interface.cpp:53-56) has no notification we could hook: detect geometry changes
-    const size_t sig = geometrySignature(scene);
-    if (g.sceneKey != scene.meshes.data() || g.sceneSig != sig) { uploadScene(scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; }
+    const uint64_t sig = geometrySignature(scene);
+    if (g.sceneDirty || g.sceneKey != scene.meshes.data() || g.sceneSig != sig) {
+        uploadScene(scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; g.sceneDirty = false;
+    }
     uploadLights(scene);
     romis_camera cam;
     const glm::vec3 pos = camera.position();                                // trackball.cpp:75-78
@@ -165,7 +234,7 @@ ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid
     const romis_features f = toPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
     // Screen::pixels() is the row-flipped float RGB framebuffer setPixel writes (screen.cpp:37-43,110-118)
-    float* out = &screen.pixels()[0].x;
+    float* out = screenStorage(screen);
     check(romis_render_frame(g.ctx, &f, &cam, res.x, res.y, previousFrameGrid ? 1 : 0, &rng, out), "romis_render_frame");
 
     // The reservoir grid lives on the device.  The caller only tests the returned grid for presence and hands a copy back
@@ -201,7 +270,7 @@ void ROMIS_DROPIN_RMIS_NAME(const Scene& scene, const Trackball& camera, const E
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    check(romis_render_frame_rmis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, &screen.pixels()[0].x), "romis_render_frame_rmis");
+    check(romis_render_frame_rmis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)), "romis_render_frame_rmis");
 }
 
 // saveAlphasVisualisation (render.cpp:227-229, BMP dumps of the per-technique alphas) is a debugging aid of the CPU path
@@ -212,5 +281,5 @@ void ROMIS_DROPIN_ROMIS_NAME(const Scene& scene, const Trackball& camera, const 
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    check(romis_render_frame_romis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, &screen.pixels()[0].x), "romis_render_frame_romis");
+    check(romis_render_frame_romis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)), "romis_render_frame_romis");
 }

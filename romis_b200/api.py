@@ -27,6 +27,8 @@ EXPORTS = [
     "romis_row_hit_counts", "romis_band_prepare", "romis_peer_export", "romis_peer_attach", "romis_peer_detach", "romis_peer_error",
     "romis_render_frame_rmis", "romis_download_rmis_neighbours", "romis_specular_cutoff",
     "romis_render_frame_romis", "romis_download_romis_system",
+    "romis_upload_lights_range", "romis_set_light_archive_auto", "romis_light_archive_marks", "romis_light_archive_release",
+    "romis_light_archive_size", "romis_host_register", "romis_host_unregister",
 ]
 PEER_BLOB_BYTES = 512
 
@@ -52,6 +54,11 @@ def load_library() -> C.CDLL:
     L.romis_destroy.argtypes = [vp]; L.romis_destroy.restype = None
     L.romis_upload_scene.argtypes = [vp, C.POINTER(abi.romis_mesh_desc), ci, C.POINTER(abi.romis_texture), ci]
     L.romis_upload_lights.argtypes = [vp, C.POINTER(abi.romis_light), ci]
+    L.romis_upload_lights_range.argtypes = [vp, C.POINTER(abi.romis_light), ci, ci, ci]
+    L.romis_set_light_archive_auto.argtypes = [vp, ci]
+    L.romis_light_archive_marks.argtypes = [vp, vp, ci, C.POINTER(ci)]
+    L.romis_light_archive_release.argtypes = [vp, vp, ci]
+    L.romis_light_archive_size.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
     frame_args = [vp, C.POINTER(abi.romis_features), C.POINTER(abi.romis_camera), ci, ci, ci, C.POINTER(abi.romis_rng)]
     L.romis_render_frame.argtypes = frame_args + [vp]
     L.romis_render_frame_device.argtypes = frame_args + [C.POINTER(vp)]
@@ -81,6 +88,7 @@ def load_library() -> C.CDLL:
     L.romis_specular_cutoff.restype = C.c_float; L.romis_specular_cutoff.argtypes = [C.c_float]
     L.romis_host_alloc.restype = vp; L.romis_host_alloc.argtypes = [C.c_size_t]
     L.romis_host_free.argtypes = [vp]; L.romis_host_free.restype = None
+    L.romis_host_register.argtypes = [vp, C.c_size_t]; L.romis_host_unregister.argtypes = [vp]
     _lib = L
     return L
 
@@ -174,9 +182,33 @@ class RestirRenderer:
         self._check(self.lib.romis_upload_scene(self.ctx, descs, nm, texs, nt))
         self.upload_lights(scene.lights)
 
-    def upload_lights(self, lights: np.ndarray):
+    def upload_lights(self, lights: np.ndarray, dirty: tuple | None = None):
+        """scene.lights as of this frame.  `dirty` = (first, count): only those lights are examined (romis_upload_lights_range)."""
         a = np.ascontiguousarray(lights, LIGHT_DTYPE)
-        self._check(self.lib.romis_upload_lights(self.ctx, a.ctypes.data_as(C.POINTER(abi.romis_light)), len(a)))
+        ptr = a.ctypes.data_as(C.POINTER(abi.romis_light))
+        if dirty is None:
+            self._check(self.lib.romis_upload_lights(self.ctx, ptr, len(a)))
+        else:
+            self._check(self.lib.romis_upload_lights_range(self.ctx, ptr, len(a), int(dirty[0]), int(dirty[1])))
+
+    # ---- light archive (history samples of edited lights; see include/romis_gpu.h) ----
+    def set_light_archive_auto(self, on: bool):
+        self._check(self.lib.romis_set_light_archive_auto(self.ctx, int(on)))
+
+    def light_archive_size(self):
+        n, held = C.c_int(), C.c_int()
+        self._check(self.lib.romis_light_archive_size(self.ctx, C.byref(n), C.byref(held)))
+        return n.value, held.value
+
+    def light_archive_marks(self) -> np.ndarray:
+        n, _ = self.light_archive_size()
+        m = np.zeros(max(n, 1), np.uint8); got = C.c_int()
+        self._check(self.lib.romis_light_archive_marks(self.ctx, m.ctypes.data, len(m), C.byref(got)))
+        return m[:got.value]
+
+    def light_archive_release(self, keep: np.ndarray):
+        k = np.ascontiguousarray(keep, np.uint8)
+        self._check(self.lib.romis_light_archive_release(self.ctx, k.ctypes.data if len(k) else None, len(k)))
 
     # ---- frame ----
     @staticmethod

@@ -100,6 +100,7 @@ class BandedRenderer:
         self._attached = None
         self.fallback_reason = None
         self.edges = None           # explicit band edges (balanced_band_edges); None = equal row counts
+        self._archive_manual = False
 
     def _attach_peers(self, features, W, H):
         """prepare -> export -> swap blobs -> attach; redone when the frame geometry changes."""
@@ -107,7 +108,7 @@ class BandedRenderer:
         if self._attached == key:
             return
         if self._attached is not None:
-            self.r.peer_detach()
+            self._detach_all()
         ok, err = 1, ""
         try:
             self.r.band_prepare(features, W, H)
@@ -137,6 +138,39 @@ class BandedRenderer:
             self._attached = None
             return
         self._attached = key
+
+    def _detach_all(self):
+        """Every rank drains its stream and closes its mappings of the neighbours' buffers; only after ALL ranks have done
+        so may any of them re-allocate or free the exported buffers (CUDA: freeing exported memory an importer still has
+        open is undefined) -- hence the barrier between detach and whatever follows (band_prepare, destroy)."""
+        self.r.peer_detach()
+        self._attached = None
+        if self.world_size > 1:
+            dist.barrier()
+
+    def close(self):
+        """Collective: detach, barrier, then destroy the context."""
+        if self._attached is not None:
+            self._detach_all()
+        self.r.close()
+
+    def upload_lights(self, lights, dirty=None):
+        """scene.lights for the next frame, on every rank.  Halo rows carry light-archive slots from band to band, so all
+        ranks recycle the same slots: the marks of every band's history are OR-ed before the release (romis_gpu.h)."""
+        import numpy as np
+        if self.world_size > 1:
+            if not self._archive_manual:
+                self.r.set_light_archive_auto(False); self._archive_manual = True
+            marks = self.r.light_archive_marks()
+            n = torch.tensor([len(marks)], dtype=torch.int64, device=self.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX)
+            n = int(n.item())
+            if n:
+                keep = torch.zeros(n, dtype=torch.uint8, device=self.device)
+                keep[:len(marks)] = torch.from_numpy(np.ascontiguousarray(marks)).to(self.device)
+                dist.all_reduce(keep, op=dist.ReduceOp.MAX)
+                self.r.light_archive_release(keep.cpu().numpy())
+        self.r.upload_lights(lights, dirty)
 
     def balance(self, camera, W: int, H: int, radius: int, miss_cost: float = 0.04):
         """Equal-COST bands for this camera: hit pixels carry the work of every pass, miss pixels short-circuit
@@ -179,7 +213,7 @@ class BandedRenderer:
             if new_edges == self.edges:
                 break
             if self._attached is not None:
-                self.r.peer_detach(); self._attached = None
+                self._detach_all()
             self.edges = new_edges
             self._height = None
         self.r.reset_history()

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
         float u = 0.0f, v = 0.0f;
         if (type != ROMIS_LIGHT_POINT) u = romis_rand_to_unit(romis_rng_rand(rk, rc++));        // light.cpp:20 / :28
         if (type == ROMIS_LIGHT_PARALLELOGRAM) v = romis_rand_to_unit(romis_rng_rand(rk, rc++)); // light.cpp:29
-        v3 pos, col; light_sample(sc.lights, li, u, v, pos, col);
+        v3 pos, col; light_sample<true>(sc, li, u, v, pos, col);
         float pdf = target_pdf(c, es, pos, col);
         float w = 0.0f;                                     // +0 / (1/L) = +0: keep 0 / x off the slow division path
         if (pdf != 0.0f) w = pow2L ? pdf * nLights : pdf / invPdf;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     res_finish(r, N, sc, c, es);
     if (fr.f.initialSamplesVisibilityCheck) {
         ROMIS_FOR_SUB(j, NT, N) {
-            v3 pos, col; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], pos, col);
+            v3 pos, col; light_sample<true>(sc, r.light[j], r.u[j], r.v[j], pos, col);
             if (!visible(sc, c, pos)) r.W[j] = 0.0f;
         }
     }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev s
     _Pragma("unroll 1") for (int j = 0; j < N && !c.miss; j++) {                   // render_utils.cpp:56-62 (rolled: one copy of the shading code)
         uint4 rec = res_rec(in, lrow, j)[x];
         if (__uint_as_float(rec.w) == 0.0f) continue;
-        v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
+        v3 pos, col; light_sample(sc, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
         v3 scol = visible(sc, c, pos) ? compute_shading(c, es, pos, col) : V3(0, 0, 0);
         scol = scale3(scol, __uint_as_float(rec.w));
         color = add3(color, scol);
@@ -152,21 +152,22 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* __restrict_
 }
 
 // unpack a reservoir buffer into the flat arrays of romis_reservoir_dump (parity read-back)
-__global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, uint32_t* light, float* u, float* v, float* W, uint32_t* M,
-                            float* pos, float* col) {
+__global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, const uint32_t* __restrict__ arch_orig, uint32_t* light, float* u, float* v,
+                            float* W, uint32_t* M, float* pos, float* col) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     for (int j = 0; j < N; j++) {
         uint4 rec = res_rec(in, y - fr.ey0, j)[x];
         size_t i = ((size_t)j * fr.H + y) * fr.W + x;
-        if (light) light[i] = rec.x;
+        // an archived record reports the light it was drawn from (its position / colour below are the light's OLD ones)
+        if (light) light[i] = (rec.x != ROMIS_NO_LIGHT && (rec.x & ROMIS_LIGHT_ARCHIVED) && arch_orig) ? arch_orig[rec.x & ~ROMIS_LIGHT_ARCHIVED] : rec.x;
         if (u) u[i] = __uint_as_float(rec.y);
         if (v) v[i] = __uint_as_float(rec.z);
         if (W) W[i] = __uint_as_float(rec.w);
         if (M) M[i] = res_m(in, y - fr.ey0, j)[x];
         if (pos || col) {
-            v3 p, c; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), p, c);
+            v3 p, c; light_sample(sc, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), p, c);
             if (pos) { pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
             if (col) { col[3 * i] = c.x; col[3 * i + 1] = c.y; col[3 * i + 2] = c.z; }
         }
@@ -199,8 +200,52 @@ void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32
 void launch_wait(cudaStream_t s, const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb, uint32_t* err) {
     if (a || b) wait_kernel<<<1, 1, 0, s>>>(a, va, b, vb, err);
 }
-void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
+void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N, const uint32_t* arch_orig,
                  uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col) {
-    dump_kernel<<<grid, block, 0, s>>>(sc, fr, in, N, light, u, v, W, M, pos, col);
+    dump_kernel<<<grid, block, 0, s>>>(sc, fr, in, N, arch_orig, light, u, v, W, M, pos, col);
+}
+
+// ------------------------------------------------------------------------------------------------
+// light edits between frames (romis_upload_lights): keep the history's samples on the lights as they WERE
+// ------------------------------------------------------------------------------------------------
+// 1. the old records of the edited lights move to their archive slots and the remap table learns where they went
+__global__ void light_archive_kernel(const float4* __restrict__ lights, float4* __restrict__ arch, uint32_t* __restrict__ remap,
+                                     const uint32_t* __restrict__ idx, const uint32_t* __restrict__ slot, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * n) return;
+    const int e = t / 6, q = t - 6 * e;
+    arch[6 * (size_t)slot[e] + q] = lights[6 * (size_t)idx[e] + q];
+    if (q == 0) remap[idx[e]] = ROMIS_LIGHT_ARCHIVED | slot[e];
+}
+// 2. every history record that holds an edited light is re-pointed to the archive slot; every archive slot still held by a
+//    record is marked (a slot no record holds now can never be held again: only the history survives a frame)
+__global__ void history_remap_kernel(ResBuf hist, int lrow0, int rows, int N, const uint32_t* __restrict__ remap, uint32_t n_remap,
+                                     uint8_t* __restrict__ mark, uint32_t n_slots) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (x >= hist.W || row >= rows) return;
+    for (int j = 0; j < N; j++) {
+        uint32_t* rec = reinterpret_cast<uint32_t*>(res_rec(hist, lrow0 + row, j) + x);
+        uint32_t li = *rec;
+        if (li == ROMIS_NO_LIGHT) continue;
+        if (!(li & ROMIS_LIGHT_ARCHIVED)) {
+            if (li >= n_remap) continue;
+            const uint32_t to = remap[li];
+            if (to == ROMIS_NO_LIGHT) continue;
+            *rec = li = to;
+        }
+        const uint32_t s = li & ~ROMIS_LIGHT_ARCHIVED;
+        if (s < n_slots) mark[s] = 1;
+    }
+}
+// 3. the remap table goes back to "nothing moved"
+__global__ void remap_clear_kernel(uint32_t* __restrict__ remap, const uint32_t* __restrict__ idx, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) remap[idx[t]] = ROMIS_NO_LIGHT;
+}
+void launch_light_archive(cudaStream_t s, const float4* lights, float4* arch, uint32_t* remap, const uint32_t* idx, const uint32_t* slot, int n,
+                          const ResBuf& hist, int lrow0, int rows, int N, uint32_t n_remap, uint8_t* mark, uint32_t n_slots) {
+    if (n > 0) light_archive_kernel<<<(6 * n + 255) / 256, 256, 0, s>>>(lights, arch, remap, idx, slot, n);
+    if (rows > 0) history_remap_kernel<<<dim3((hist.W + 255) / 256, rows), 256, 0, s>>>(hist, lrow0, rows, N, remap, n_remap, mark, n_slots);
+    if (n > 0) remap_clear_kernel<<<(n + 255) / 256, 256, 0, s>>>(remap, idx, n);
 }
 }  // namespace romis

@@ -43,7 +43,7 @@ struct RmisWindow { int x0, x1, y0, y1, x, y; uint32_t mask[ROMIS_RMIS_WORDS]; }
 // unsampled^2 fits the 32-bit engine range (__gen_two_uniform_ints).  all = true copies the class without draws
 // (neighbour_selection.cpp:80).  Appends packed (y << 16 | x) entries at plane `no` of the pixel's neighbour column.
 __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32_t size, uint32_t n, bool all,
-                                           romis_stream_key ek, uint32_t& ec, uint32_t* __restrict__ col, size_t plane, int& no) {
+                                           romis_stream_key ek, uint32_t& ec, uint32_t* __restrict__ col, size_t plane, int& no, int cap) {
     if (size == 0u) return;
     if (n > size) n = size;
     if (all) n = size;
@@ -73,7 +73,10 @@ __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32
                     --unsampled; take = p0 < n;
                 } else { --unsampled; take = lemire32(ek, ec, unsampled + 1u) < n; }
             }
-            if (take) { col[(size_t)no * plane] = ((uint32_t)ny << 16) | (uint32_t)nx; no++; --n; if (n == 0u) break; }
+            if (take) {
+                if (no < cap) col[(size_t)no * plane] = ((uint32_t)ny << 16) | (uint32_t)nx;    // the grid holds k + 1 planes (host rejects what needs more)
+                no++; --n; if (n == 0u) break;
+            }
         }
     }
 }
@@ -119,15 +122,15 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
         const uint32_t ku = (uint32_t)k;
         if (rm.p.neighbourSelectionStrategy == ROMIS_NEIGHBOURS_SIMILAR) {          // :79-85
             if (ns < ku) {
-                emit_class(w, true, ns, ns, true, ek, ec, col, rm.plane, no);
-                emit_class(w, false, nd, ku - ns, false, ek, ec, col, rm.plane, no);
-            } else emit_class(w, true, ns, ku, false, ek, ec, col, rm.plane, no);
+                emit_class(w, true, ns, ns, true, ek, ec, col, rm.plane, no, rm.K1);
+                emit_class(w, false, nd, ku - ns, false, ek, ec, col, rm.plane, no, rm.K1);
+            } else emit_class(w, true, ns, ku, false, ek, ec, col, rm.plane, no, rm.K1);
         } else {                                                                    // EqualSimilarDissimilar :94-103
             uint32_t similarsSampled = min(ku / 2u + 1u, ns);
             const uint32_t desiredDissimilars = ku - similarsSampled;
             if (desiredDissimilars > nd) similarsSampled += ku - nd - similarsSampled;
-            emit_class(w, true, ns, similarsSampled, false, ek, ec, col, rm.plane, no);
-            emit_class(w, false, nd, ku - similarsSampled, false, ek, ec, col, rm.plane, no);
+            emit_class(w, true, ns, similarsSampled, false, ek, ec, col, rm.plane, no, rm.K1);
+            emit_class(w, false, nd, ku - similarsSampled, false, ek, ec, col, rm.plane, no, rm.K1);
         }
     }
     for (; no < rm.K1; no++) col[(size_t)no * rm.plane] = 0xffffffffu;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_GATHER) rmis_gather_kernel(Sce
             const float Wj = __uint_as_float(rec.w);
             // W == 0 contributes (+-0) whatever the weight and the visibility: the sum keeps its bits
             if (Wj == 0.0f) continue;
-            v3 pos, col; light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
+            v3 pos, col; light_sample<true>(sc, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), pos, col);
             const v3 shading = compute_shading(c, es, pos, col);
             if (shading.x == 0.0f && shading.y == 0.0f && shading.z == 0.0f) continue;      // same: adds (+-0)
             float misWeight = equalWeight;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
         v3 spos[CAP], scol[CAP];
         ROMIS_FOR_SUB(j, NT, N) {
             const uint4 rec = res_rec(in, ay, j)[ax];
-            light_sample(sc.lights, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), spos[j], scol[j]);
+            light_sample<true>(sc, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), spos[j], scol[j]);
         }
         // The samples shaded at this pixel (:184-186), once: the value is also distribution 0's target pdf (plane 0 of the
         // neighbour grid is the pixel itself, neighbour_selection.cpp:40,71).

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         // reservoir.cpp:84-103: Z_j = sum of totalM(s) over stream reservoirs s whose OWN pixel sees y_j with pdf > 0
         uint64_t Z[CAP];
         v3 spos[CAP], scol[CAP];
-        ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc.lights, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
+        ROMIS_FOR_SUB(j, NT, N) { Z[j] = 0ull; light_sample(sc, r.light[j], r.u[j], r.v[j], spos[j], scol[j]); }
         for (int s = 0; s < ns; s++) {
             int srow = (int)(stream[s] >> 16), sx = (int)(stream[s] & 0xffffu);
             int sy = srow + fr.ey0;

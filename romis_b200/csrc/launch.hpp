@@ -25,8 +25,10 @@ void launch_halo_push(cudaStream_t s, const void* src_low, void* dst_low, size_t
                       const uint32_t* wait_a, const uint32_t* wait_b, uint32_t* err, unsigned int* ticket);
 void launch_signal(cudaStream_t s, uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb);
 void launch_wait(cudaStream_t s, const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb, uint32_t* err);
-void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N,
+void launch_dump(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const ResBuf& in, int N, const uint32_t* arch_orig,
                  uint32_t* light, float* u, float* v, float* W, uint32_t* M, float* pos, float* col);
+void launch_light_archive(cudaStream_t s, const float4* lights, float4* arch, uint32_t* remap, const uint32_t* idx, const uint32_t* slot, int n,
+                          const ResBuf& hist, int lrow0, int rows, int N, uint32_t n_remap, uint8_t* mark, uint32_t n_slots);
 }  // namespace romis
 
 // numSamplesInReservoir 1..4 get register-resident instantiations; anything else the generic one

@@ -110,7 +110,7 @@ template <int NT> __device__ __forceinline__ void stream_sample(SubRes<NT>& r, i
     float u = __uint_as_float(rec.y), v = __uint_as_float(rec.z), Wi = __uint_as_float(rec.w);
     float pdf;
     if (own_pdf >= 0.0f && rec.x != ROMIS_NO_LIGHT) pdf = own_pdf;
-    else { v3 pos, col; light_sample(sc.lights, rec.x, u, v, pos, col); pdf = target_pdf(c, es, pos, col); }
+    else { v3 pos, col; light_sample(sc, rec.x, u, v, pos, col); pdf = target_pdf(c, es, pos, col); }
     int idx = res_update(r, N, rec.x, u, v, pdf, pdf * Wi * (float)Mi, rk, rc);
     if (NT > 0) { ROMIS_FOR_SUB(j, NT, N) { if (j == idx) r.cnt[j] = sat_add_u32(r.cnt[j], Mi); } }
     else r.cnt[idx] = sat_add_u32(r.cnt[idx], Mi);

@@ -90,9 +90,17 @@ struct romis_ctx {
     // timing
     bool stage_timing = false;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<float4> light_shadow;   // host copy of the packed light table on the device (dirty tracking)
-    void* light_stage = nullptr; size_t light_stage_bytes = 0;     // pinned staging of the packed light table
+    // lights (see "light table maintenance")
+    float4* light_mirror = nullptr; size_t light_cap = 0;          // pinned mirror of the device table, capacity in lights
     cudaEvent_t ev_lights = nullptr; bool light_copy_pending = false;
+    std::vector<uint32_t> lights_changed, lights_gone;
+    DevBuf lights_arch, light_remap, arch_mark, arch_orig_dev, dirty_dev;
+    size_t arch_cap = 0;                                            // archive slots allocated on the device
+    std::vector<uint32_t> arch_orig;                                // per slot: the light it was archived from, 0xffffffff = free
+    std::vector<uint32_t> arch_free;
+    uint8_t* arch_mark_host = nullptr; uint32_t marks_slots = 0; bool marks_pending = false; cudaEvent_t ev_marks = nullptr;
+    uint32_t* dirty_stage = nullptr; size_t dirty_stage_cap = 0;
+    bool arch_auto = true;
     cudaStream_t copy_stream = nullptr;     // image read-back, overlapped with shading (romis_frame_end)
     cudaEvent_t ev_chunk[8] = {};
     std::vector<cudaEvent_t> ev_stage;  // begin, after primary, after initial, after temporal, after spatial p..., after shade
@@ -158,6 +166,7 @@ extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** ou
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_lights, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_marks, cudaEventDisableTiming);
     for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->ev_chunk[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { set_err(std::string("context setup: ") + cudaGetErrorString(e)); delete c; return ROMIS_ERR_CUDA; }
     *out = c;
@@ -170,7 +179,8 @@ extern "C" void romis_destroy(romis_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
-                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_pv, &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib, &c->romis_alpha}) b->release();
+                      &c->gb_tn, &c->gb_mesh, &c->gb_uv, &c->rgb, &c->res[0], &c->res[1], &c->res[2], &c->rmis_pv, &c->rmis_nb, &c->rmis_acc, &c->romis_wsum, &c->romis_chosen, &c->romis_tech, &c->romis_contrib, &c->romis_alpha,
+                      &c->lights_arch, &c->light_remap, &c->arch_mark, &c->arch_orig_dev, &c->dirty_dev}) b->release();
     romis_peer_detach(c);
     c->flags.release();
     for (auto& kv : c->captured) kv.second.release();
@@ -180,7 +190,10 @@ extern "C" void romis_destroy(romis_ctx* c) {
     for (int k = 0; k < 8; k++) if (c->ev_chunk[k]) cudaEventDestroy(c->ev_chunk[k]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_lights) cudaEventDestroy(c->ev_lights);
-    if (c->light_stage) cudaFreeHost(c->light_stage);
+    if (c->ev_marks) cudaEventDestroy(c->ev_marks);
+    if (c->light_mirror) cudaFreeHost(c->light_mirror);
+    if (c->arch_mark_host) cudaFreeHost(c->arch_mark_host);
+    if (c->dirty_stage) cudaFreeHost(c->dirty_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -224,6 +237,7 @@ extern "C" int romis_upload_scene(romis_ctx* c, const romis_mesh_desc* meshes, i
     if (!c) return ROMIS_ERR_INVALID;
     if (n_meshes < 0 || n_textures < 0 || (n_meshes > 0 && !meshes) || (n_textures > 0 && !textures))
         return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: bad arguments");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_upload_scene: frame in flight");
     RCHECK(c, cudaSetDevice(c->device));
     size_t ntri = 0;
     for (int m = 0; m < n_meshes; m++) {
@@ -318,43 +332,196 @@ static void pack_light(const romis_light& l, float4* r) {
     r[5] = make_float4(l.c2[0], l.c2[1], l.c2[2], 0.0f);
 }
 
-extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) {
-    if (!c) return ROMIS_ERR_INVALID;
-    if (n < 0 || (n > 0 && !lights)) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: bad arguments");
-    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_upload_lights: frame in flight");
-    RCHECK(c, cudaSetDevice(c->device));
-    for (int i = 0; i < n; i++)
-        if (lights[i].type > ROMIS_LIGHT_PARALLELOGRAM) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: unknown light type");
-    // Called every frame by the drop-in (the reference re-reads scene.lights every frame and the UI edits them without
-    // notification, ui.cpp:172-261), so dirty tracking lives here: the packed table is compared with the one on the
-    // device and an unchanged table costs no transfer.  A changed table is packed into a pinned staging buffer and copied
-    // on the context's stream, ordered before the next frame's kernels, without a host synchronisation.
-    const size_t count = 6 * (size_t)n;
-    std::vector<float4> packed(std::max<size_t>(6, count));
-    for (int i = 0; i < n; i++) pack_light(lights[i], &packed[6 * (size_t)i]);
-    if (c->sc.lights && c->sc.n_lights == n && c->light_shadow.size() == packed.size() &&
-        std::memcmp(c->light_shadow.data(), packed.data(), packed.size() * sizeof(float4)) == 0)
-        return ROMIS_OK;
-    // The history stores (light index, u, v): with fewer lights than before, stored indices could point past the table.
-    if (n < c->sc.n_lights) c->history_valid = false;
-    const size_t bytes = sizeof(float4) * packed.size();
-    if (c->light_stage_bytes < bytes) {
-        RCHECK(c, cudaStreamSynchronize(c->stream));
-        if (c->light_stage) cudaFreeHost(c->light_stage);
-        c->light_stage = nullptr; c->light_stage_bytes = 0;
-        RCHECK(c, cudaMallocHost(&c->light_stage, bytes));
-        c->light_stage_bytes = bytes;
-        RCHECK(c, c->lights.ensure(bytes));
-    } else if (c->light_copy_pending) {
-        RCHECK(c, cudaEventSynchronize(c->ev_lights));      // the previous copy out of the staging buffer (long done)
+// ---- light table maintenance ----
+// The packed table lives three times: on the device (sc.lights), as a pinned host mirror (light_mirror: what the device holds
+// once the copies in flight have landed; also the staging area of those copies) and in the caller's Scene.  The reference reads
+// scene.lights fresh every frame and the UI edits them without notification (light.cpp:46-66, ui.cpp:172-261), so the drop-in
+// hands the table over every frame and dirty tracking lives here.
+//
+// What an edit means for the temporal history: the reference's reservoirs hold LightSample{position, color} by value
+// (reservoir.h:18-26) and temporalReuse streams the predecessor's samples as stored (render_utils.cpp:154-170), so a sample
+// drawn from a light keeps that light's OLD position / colour however the light is edited or removed afterwards, for as long
+// as it survives resampling.  The records here hold (light, u, v); to stay bit-identical, the old record of every edited or
+// removed light is copied (device to device) into an archive slot and the history records that hold the light are re-pointed to
+// the slot (launch_light_archive), before the new record overwrites the old.  The same pass marks which slots are still held;
+// unheld slots are recycled at the next edit (a slot no history record holds can never be held again).
+static int grow_light_tables(romis_ctx* c, size_t need) {
+    if (need <= c->light_cap) return ROMIS_OK;
+    size_t cap = std::max<size_t>(std::max<size_t>(need, 64), c->light_cap + c->light_cap / 2);
+    float4* m = nullptr;
+    RCHECK(c, cudaStreamSynchronize(c->stream));
+    RCHECK(c, cudaMallocHost((void**)&m, cap * 6 * sizeof(float4)));
+    if (c->light_mirror) { std::memcpy(m, c->light_mirror, c->light_cap * 6 * sizeof(float4)); cudaFreeHost(c->light_mirror); }
+    c->light_mirror = m;
+    RCHECK(c, c->lights.ensure(cap * 6 * sizeof(float4)));
+    RCHECK(c, c->light_remap.ensure(cap * sizeof(uint32_t)));
+    RCHECK(c, cudaMemsetAsync(c->light_remap.p, 0xff, cap * sizeof(uint32_t), c->stream));
+    c->light_cap = cap;
+    c->sc.lights = (const float4*)c->lights.p;
+    return ROMIS_OK;
+}
+
+static void archive_free_all(romis_ctx* c) {
+    c->arch_free.clear();
+    for (size_t s = c->arch_orig.size(); s-- > 0;) { c->arch_orig[s] = 0xffffffffu; c->arch_free.push_back((uint32_t)s); }
+    c->marks_pending = false;
+}
+
+// recycle the slots the last edit's mark pass found unheld (keep == nullptr: this context's own marks)
+static int archive_harvest(romis_ctx* c, const uint8_t* keep, uint32_t n_slots) {
+    if (!keep) {
+        if (!c->marks_pending) return ROMIS_OK;
+        RCHECK(c, cudaEventSynchronize(c->ev_marks));
+        keep = c->arch_mark_host; n_slots = c->marks_slots;
     }
-    std::memcpy(c->light_stage, packed.data(), bytes);
-    RCHECK(c, cudaMemcpyAsync(c->lights.p, c->light_stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    for (uint32_t s = 0; s < n_slots && s < c->arch_orig.size(); s++)
+        if (c->arch_orig[s] != 0xffffffffu && !keep[s]) { c->arch_orig[s] = 0xffffffffu; c->arch_free.push_back(s); }
+    c->marks_pending = false;
+    return ROMIS_OK;
+}
+
+static int archive_lights(romis_ctx* c, const std::vector<uint32_t>& gone) {
+    if (c->arch_auto) { int rc = archive_harvest(c, nullptr, 0); if (rc) return rc; }
+    const size_t n = gone.size();
+    // pinned staging of {light, slot} pairs
+    if (c->dirty_stage_cap < 2 * n) {
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+        if (c->dirty_stage) cudaFreeHost(c->dirty_stage);
+        c->dirty_stage = nullptr; c->dirty_stage_cap = 0;
+        RCHECK(c, cudaMallocHost((void**)&c->dirty_stage, 2 * n * sizeof(uint32_t)));
+        c->dirty_stage_cap = 2 * n;
+        RCHECK(c, c->dirty_dev.ensure(2 * n * sizeof(uint32_t)));
+    }
+    for (size_t k = 0; k < n; k++) {
+        uint32_t slot;
+        if (!c->arch_free.empty()) { slot = c->arch_free.back(); c->arch_free.pop_back(); }
+        else { slot = (uint32_t)c->arch_orig.size(); c->arch_orig.push_back(0xffffffffu); }
+        c->arch_orig[slot] = gone[k];
+        c->dirty_stage[k] = gone[k]; c->dirty_stage[n + k] = slot;
+    }
+    const size_t slots = c->arch_orig.size();
+    if (slots >= 0x7fffffffu) return fail(c, ROMIS_ERR_NOMEM, "light archive full");
+    if (slots > c->arch_cap) {                          // grow the device archive, keeping what it holds
+        const size_t cap = std::max<size_t>(std::max<size_t>(slots, 256), 2 * c->arch_cap);
+        DevBuf bigger, orig, mark;
+        RCHECK(c, bigger.ensure(cap * 6 * sizeof(float4)));
+        RCHECK(c, orig.ensure(cap * sizeof(uint32_t)));
+        RCHECK(c, mark.ensure(cap));
+        if (c->arch_cap) RCHECK(c, cudaMemcpyAsync(bigger.p, c->lights_arch.p, c->arch_cap * 6 * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+        c->lights_arch.release(); c->arch_orig_dev.release(); c->arch_mark.release();
+        c->lights_arch = bigger; c->arch_orig_dev = orig; c->arch_mark = mark;
+        if (c->arch_mark_host) cudaFreeHost(c->arch_mark_host);
+        c->arch_mark_host = nullptr;
+        RCHECK(c, cudaMallocHost((void**)&c->arch_mark_host, cap));
+        c->arch_cap = cap;
+        c->sc.lights_arch = (const float4*)c->lights_arch.p;
+    }
+    RCHECK(c, cudaMemcpyAsync(c->dirty_dev.p, c->dirty_stage, 2 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    RCHECK(c, cudaMemcpyAsync(c->arch_orig_dev.p, c->arch_orig.data(), slots * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    RCHECK(c, cudaMemsetAsync(c->arch_mark.p, 0, slots, c->stream));
+    ResBuf h; h.base = (unsigned char*)c->res[c->hist].p; h.row_stride = c->row_stride; h.W = c->W; h.N = c->N;
+    launch_light_archive(c->stream, (const float4*)c->lights.p, (float4*)c->lights_arch.p, (uint32_t*)c->light_remap.p,
+                         (const uint32_t*)c->dirty_dev.p, (const uint32_t*)c->dirty_dev.p + n, (int)n,
+                         h, c->y0 - c->ey0, c->y1 - c->y0, c->N, (uint32_t)c->light_cap, (uint8_t*)c->arch_mark.p, (uint32_t)slots);
+    RCHECK(c, cudaGetLastError());
+    RCHECK(c, cudaMemcpyAsync(c->arch_mark_host, c->arch_mark.p, slots, cudaMemcpyDeviceToHost, c->stream));
+    RCHECK(c, cudaEventRecord(c->ev_marks, c->stream));
+    c->marks_pending = true; c->marks_slots = (uint32_t)slots;
+    // the pageable arch_orig copy above and the pinned pair list must not be rewritten before they are read
     RCHECK(c, cudaEventRecord(c->ev_lights, c->stream));
     c->light_copy_pending = true;
-    c->light_shadow.swap(packed);
+    return ROMIS_OK;
+}
+
+// lights[first .. first + count) may differ from what the device holds; everything else is known to be unchanged
+static int upload_lights_impl(romis_ctx* c, const romis_light* lights, int n, int first, int count) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (n < 0 || (n > 0 && !lights) || n >= 0x7fffffff) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: bad arguments");
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_upload_lights: frame in flight");
+    const int old_n = c->sc.n_lights;
+    if (n != old_n || first < 0 || count < 0 || first > n || count > n - first) { first = 0; count = n; }
+    for (int i = first; i < first + count; i++)
+        if (lights[i].type > ROMIS_LIGHT_PARALLELOGRAM) return fail(c, ROMIS_ERR_INVALID, "romis_upload_lights: unknown light type");
+    RCHECK(c, cudaSetDevice(c->device));
+    if (c->light_copy_pending) { RCHECK(c, cudaEventSynchronize(c->ev_lights)); c->light_copy_pending = false; }   // copies out of the mirror: long done
+
+    // 1. which lights changed (bitwise, on the packed record)
+    std::vector<uint32_t>& changed = c->lights_changed; changed.clear();
+    std::vector<uint32_t>& gone = c->lights_gone; gone.clear();      // edited or removed: their old records matter to the history
+    const int common = std::min(n, old_n);
+    float4 tmp[6];
+    for (int i = first; i < std::min(first + count, common); i++) {
+        pack_light(lights[i], tmp);
+        if (std::memcmp(c->light_mirror + 6 * (size_t)i, tmp, sizeof tmp) != 0) { changed.push_back((uint32_t)i); gone.push_back((uint32_t)i); }
+    }
+    for (int i = n; i < old_n; i++) gone.push_back((uint32_t)i);
+    if (changed.empty() && n == old_n && c->sc.lights) return ROMIS_OK;
+
+    // 2. the history keeps the old records (before anything overwrites them on the device)
+    if (!c->history_valid || !c->W) archive_free_all(c);
+    else if (!gone.empty()) { int rc = archive_lights(c, gone); if (rc) return rc; }
+
+    // 3. new records: into the mirror, then the changed runs (or the whole table after a re-allocation) to the device
+    const size_t cap_before = c->light_cap;
+    int rc = grow_light_tables(c, (size_t)std::max(n, 1));
+    if (rc) return rc;
+    const bool all = c->light_cap != cap_before;
+    for (uint32_t i : changed) pack_light(lights[i], c->light_mirror + 6 * (size_t)i);
+    for (int i = old_n; i < n; i++) { pack_light(lights[i], c->light_mirror + 6 * (size_t)i); changed.push_back((uint32_t)i); }
+    auto send = [&](size_t a, size_t b) {       // lights [a, b)
+        return cudaMemcpyAsync((float4*)c->lights.p + 6 * a, c->light_mirror + 6 * a, (b - a) * 6 * sizeof(float4), cudaMemcpyHostToDevice, c->stream);
+    };
+    if (all) { if (n > 0) RCHECK(c, send(0, (size_t)n)); }
+    else if (!changed.empty()) {
+        size_t runs = 1;
+        for (size_t k = 1; k < changed.size(); k++) runs += changed[k] != changed[k - 1] + 1;
+        if (runs > 16) RCHECK(c, send(changed.front(), (size_t)changed.back() + 1));
+        else for (size_t k = 0; k < changed.size();) {
+            size_t e = k + 1;
+            while (e < changed.size() && changed[e] == changed[e - 1] + 1) e++;
+            RCHECK(c, send(changed[k], (size_t)changed[e - 1] + 1));
+            k = e;
+        }
+    }
+    RCHECK(c, cudaEventRecord(c->ev_lights, c->stream));
+    c->light_copy_pending = true;
     c->sc.lights = (const float4*)c->lights.p;
+    c->sc.lights_arch = (const float4*)c->lights_arch.p;
     c->sc.n_lights = n;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) { return upload_lights_impl(c, lights, n, 0, n); }
+
+extern "C" int romis_upload_lights_range(romis_ctx* c, const romis_light* lights, int n, int first_dirty, int n_dirty) {
+    return upload_lights_impl(c, lights, n, first_dirty, n_dirty);
+}
+
+extern "C" int romis_set_light_archive_auto(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->arch_auto = on != 0; return ROMIS_OK; }
+
+extern "C" int romis_light_archive_marks(romis_ctx* c, uint8_t* marks, int capacity, int* n_slots) {
+    if (!c || !n_slots || capacity < 0 || (capacity > 0 && !marks)) return ROMIS_ERR_INVALID;
+    *n_slots = 0;
+    if (!c->marks_pending) return ROMIS_OK;
+    RCHECK(c, cudaSetDevice(c->device));
+    RCHECK(c, cudaEventSynchronize(c->ev_marks));
+    if ((uint32_t)capacity < c->marks_slots) return fail(c, ROMIS_ERR_INVALID, "romis_light_archive_marks: buffer too small");
+    std::memcpy(marks, c->arch_mark_host, c->marks_slots);
+    *n_slots = (int)c->marks_slots;
+    return ROMIS_OK;
+}
+
+extern "C" int romis_light_archive_release(romis_ctx* c, const uint8_t* keep, int n_slots) {
+    if (!c || n_slots < 0 || (n_slots > 0 && !keep)) return ROMIS_ERR_INVALID;
+    if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_light_archive_release: frame in flight");
+    return archive_harvest(c, keep, (uint32_t)n_slots);
+}
+
+extern "C" int romis_light_archive_size(romis_ctx* c, int* n_slots, int* n_held) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (n_slots) *n_slots = (int)c->arch_orig.size();
+    if (n_held) *n_held = (int)(c->arch_orig.size() - c->arch_free.size());
     return ROMIS_OK;
 }
 
@@ -380,6 +547,8 @@ static int validate(romis_ctx* c, const romis_features* f, const romis_camera* c
     if (f->initialLightSamples < 1) return fail(c, ROMIS_ERR_INVALID, "initialLightSamples must be >= 1");
     if (f->numNeighboursToSample > ROMIS_MAX_K) return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample must be <= 32");
     if (f->spatialResampleRadius > 4096) return fail(c, ROMIS_ERR_INVALID, "spatialResampleRadius must be <= 4096");
+    // random-stream stages ROMIS_STAGE_SPATIAL0 + pass must stay below ROMIS_STAGE_RMIS_NEIGH (include/romis_rng.h); the UI allows 1..5
+    if (f->spatialReuse && f->spatialResamplingPasses > 61) return fail(c, ROMIS_ERR_INVALID, "spatialResamplingPasses must be <= 61");
     if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
     return ROMIS_OK;
 }
@@ -767,6 +936,10 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR)
         return fail(c, ROMIS_ERR_INVALID, "NeighbourSelectionStrategy::Dissimilar is undefined behaviour in the reference (neighbour_selection.cpp:88-93)");
     if (rp->neighbourSelectionStrategy > ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR) return fail(c, ROMIS_ERR_INVALID, "unknown neighbour selection strategy");
+    // k = 0 with EqualSimilarDissimilar: `numNeighboursToSample - similarsSampled` wraps in the reference's unsigned arithmetic
+    // (neighbour_selection.cpp:95-98) and std::sample then takes the WHOLE window (up to (2r+1)^2 - 1 pixels per pixel)
+    if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR && f->numNeighboursToSample == 0)
+        return fail(c, ROMIS_ERR_INVALID, "numNeighboursToSample = 0 with EqualSimilarDissimilar is unsigned wrap-around in the reference (neighbour_selection.cpp:95-98)");
     if (rp->neighbourSelectionStrategy != ROMIS_NEIGHBOURS_RANDOM && f->spatialResampleRadius > ROMIS_RMIS_MAX_R)
         return fail(c, ROMIS_ERR_INVALID, "spatialResampleRadius must be <= 30 for similarity-based neighbour selection (ui.cpp:308)");
     if (rp->maxIterationsMIS > 0x7fffffffu - ROMIS_STAGE_RMIS_INITIAL0) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS too large");
@@ -944,7 +1117,7 @@ extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
                 case 1: t.primary_ms = ms; break;
                 case 2: t.initial_ms = ms; break;
                 case 3: t.temporal_ms = ms; break;
-                case 4: if (c->marks[i].idx < 8) t.spatial_ms[c->marks[i].idx] = ms; t.n_spatial = std::max(t.n_spatial, c->marks[i].idx + 1); break;
+                case 4: if (c->marks[i].idx < 8) t.spatial_ms[c->marks[i].idx] = ms; t.n_spatial = std::min(8, std::max(t.n_spatial, c->marks[i].idx + 1)); break;
                 case 5: t.shade_ms = ms; break;
                 case 6: if (c->marks[i].idx < 8) t.exchange_ms[c->marks[i].idx] = ms; break;
                 case 7: t.neighbours_ms = ms; break;
@@ -985,7 +1158,7 @@ extern "C" int romis_download_reservoirs(romis_ctx* c, int pass_id, romis_reserv
     }
     if (rc == ROMIS_OK) {
         ResBuf b; b.base = (unsigned char*)src; b.row_stride = c->row_stride; b.W = c->W; b.N = c->N;
-        launch_dump(c->stream, grid_for(c->W, c->y1 - c->y0), kBlock, c->sc, c->fr, b, c->N, (uint32_t*)slots[0].dev, (float*)slots[1].dev,
+        launch_dump(c->stream, grid_for(c->W, c->y1 - c->y0), kBlock, c->sc, c->fr, b, c->N, (const uint32_t*)c->arch_orig_dev.p, (uint32_t*)slots[0].dev, (float*)slots[1].dev,
                     (float*)slots[2].dev, (float*)slots[3].dev, (uint32_t*)slots[4].dev, (float*)slots[5].dev, (float*)slots[6].dev);
         cudaError_t e = cudaGetLastError();
         for (auto& s : slots) if (s.host && e == cudaSuccess) e = cudaMemcpyAsync(s.host, s.dev, n * s.elem, cudaMemcpyDeviceToHost, c->stream);
@@ -1057,3 +1230,13 @@ extern "C" void* romis_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void romis_host_free(void* p) { if (p) cudaFreeHost(p); }
+// Page-locks memory the caller already owns (the reference's Screen keeps its pixels in a std::vector, screen.h): the image
+// read-back of romis_render_frame into it then runs as asynchronous DMA.
+extern "C" int romis_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return ROMIS_ERR_INVALID;
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? ROMIS_OK : (cudaGetLastError(), ROMIS_ERR_CUDA);
+}
+extern "C" int romis_host_unregister(void* p) {
+    if (!p) return ROMIS_ERR_INVALID;
+    return cudaHostUnregister(p) == cudaSuccess ? ROMIS_OK : (cudaGetLastError(), ROMIS_ERR_CUDA);
+}

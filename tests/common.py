@@ -86,3 +86,19 @@ def assert_solve_tolerance(a, b, what):
     on the nightclub: 5.6 % of the channels beyond 1e-4, 1.2 % beyond 1e-3, 0.3 % beyond 1e-2, none beyond 1e-1."""
     assert_mostly_close(a, b, 1e-3, 0.03, what + " (1e-3 tier)")
     assert_mostly_close(a, b, 1e-1, 0.003, what + " (1e-1 tier)")
+
+
+def assert_image_rmse(a, b, bar, what):
+    """north_star's image bar: RMSE <= 1e-3 over the whole image AS PRESENTED -- the Screen clamps every channel to [0, 1] when
+    it writes or shows the framebuffer (reference src/rendering/screen.cpp:45-56).  (The R-OMIS solve yields negative radiance
+    in a few pixels, which the exposure tone map turns into -1e6 or -inf: off-screen either way.)  NaN channels (0 / 0 in the
+    reference's solve) must sit at the same places on both sides and are left out of the mean."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, f"{what}: shape"
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb), f"{what}: NaN channels at different places ({na.sum()} vs {nb.sum()})"
+    ok = ~na
+    ca, cb = np.clip(a[ok], 0.0, 1.0), np.clip(b[ok], 0.0, 1.0)
+    rmse = float(np.sqrt(np.mean((ca - cb) ** 2))) if ok.any() else 0.0
+    assert rmse <= bar, f"{what}: RMSE {rmse:.3e} > {bar:.0e}"
+    return rmse

@@ -103,6 +103,34 @@ def test_c3_many_lights_row_bands(oracle_factory, unbiased):
             b.close()
 
 
+@pytest.mark.parametrize("n_lights", [65536, 1 << 20, 100003])
+@pytest.mark.parametrize("unbiased", [False, True])
+def test_c3_c5_full_light_counts(oracle_factory, n_lights, unbiased):
+    """The light counts BASELINE C3 (65 536) and C5 (2^20) name, at a small resolution: the power-of-two shortcut of the initial
+    weight (pdf * L instead of pdf / (1 / L)), the light pick at large ranges and the 96-byte record gather, biased and unbiased
+    + visibility; 100 003 lights take the division route."""
+    from romis_b200.api import RestirRenderer
+    scene = load_scene("Monkey")
+    scene.lights = synthetic_lights(n_lights, seed=3, intensity=24.0)
+    feat = Features(spatialResamplingPasses=2, initialSamplesVisibilityCheck=True,
+                    unbiasedCombination=unbiased, spatialReuseVisibilityCheck=unbiased)
+    W, H = 96, 64
+    cam = CORNELL_CAM.to_abi(W, H)
+    r = RestirRenderer(0); r.upload_scene(scene)
+    orc = oracle_factory(); orc.upload_scene(scene); orc.reset_history()
+    try:
+        for f in range(2):
+            oimg = orc.render_frame(feat, cam, W, H, f > 0, 17, f)
+            gimg = r.render_frame(feat, cam, W, H, f > 0, 17, f)
+            final_state_equal(f"L={n_lights} unbiased={unbiased} frame {f}", r, orc)
+            assert_bits_equal(gimg, oimg, f"L={n_lights} unbiased={unbiased} frame {f} image")
+        ids = r.reservoirs(abi.ROMIS_PASS_FINAL).light_id
+        held = ids[ids != 0xFFFFFFFF]
+        assert held.size and held.max() < n_lights and held.max() > n_lights // 2     # picks span the whole table
+    finally:
+        r.close()
+
+
 def test_mid_size_unbiased_multi_frame(oracle_factory):
     """A larger unbiased + visibility run (rare paths: Z = 0, empty sub-reservoirs, generic N)."""
     from romis_b200.api import RestirRenderer

@@ -9,7 +9,7 @@ from oracle import pyoracle
 from romis_b200 import abi
 from romis_b200.scene import Features, RmisParams
 from cases import CORNELL_CAM, NIGHTCLUB_CAM
-from common import assert_bits_equal, assert_solve_tolerance, load_scene
+from common import assert_bits_equal, assert_image_rmse, assert_solve_tolerance, load_scene
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(pyoracle.DROPIN_SO), reason="oracle/_ref/libromis_dropin.so not built (make -C oracle dropin)")]
@@ -46,3 +46,4 @@ def test_dropin_rmis_and_romis_fill_the_reference_screen():
     cpu, _A, _B = lib.render_frame_romis(feat, rp, NIGHTCLUB_CAM, W, H, 2718, 2, False)
     gpu = lib.render_frame_mis_gpu(True, feat, rp, NIGHTCLUB_CAM, W, H, 2718, 2)
     assert_solve_tolerance(gpu, cpu, "Screen::pixels() of the GPU renderROMIS vs the reference's")
+    assert_image_rmse(gpu, cpu, 1e-3, "Screen::pixels() of the GPU renderROMIS vs the reference's (RMSE)")

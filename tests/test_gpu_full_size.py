@@ -1,6 +1,7 @@
 """CUDA path at BASELINE.json's full size (configs[1]: nightclub 1920x1080, M=32, temporal + 3 spatial, visibility reuse):
-size-independent properties (the oracle cannot run this size in seconds) + bit-exact agreement with the oracle on a
-sub-window of rows rendered as a band."""
+the WHOLE frame against the oracle (OpenMP on the host cores, ~10 s per frame) -- final light index / u / v / M / W of every
+sub-reservoir and the image, bit for bit, over two frames (the second exercises the temporal pass) -- plus size-independent
+invariants, run-to-run determinism and the equivalence of a 3-band split with the single-context frame."""
 import numpy as np
 import pytest
 
@@ -11,6 +12,29 @@ from common import assert_bits_equal, load_scene
 from test_oracle_properties import check_frame_invariants
 
 pytestmark = pytest.mark.gpu
+
+
+def test_full_size_c2_matches_the_oracle_bit_for_bit(oracle_factory):
+    """BASELINE configs[1] as quoted: 1920x1080, M=32, N=2, temporal + 3 spatial passes k=5 r=10, visibility reuse."""
+    from romis_b200.api import RestirRenderer
+    scene = load_scene("CornellNightClub")
+    feat = Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True)
+    W, H = 1920, 1080
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    r = RestirRenderer(0); r.upload_scene(scene)
+    orc = oracle_factory(); orc.upload_scene(scene); orc.reset_history()
+    try:
+        for fr in range(2):
+            gimg = r.render_frame(feat, cam, W, H, fr > 0, 2024, fr)
+            oimg = orc.render_frame(feat, cam, W, H, fr > 0, 2024, fr)
+            g, o = r.reservoirs(abi.ROMIS_PASS_FINAL), orc.reservoirs(abi.ROMIS_PASS_FINAL)
+            for fld in ("light_id", "M", "u", "v", "W"):
+                assert_bits_equal(getattr(g, fld), getattr(o, fld), f"1080p frame {fr} final {fld}")
+            assert_bits_equal(gimg, oimg, f"1080p frame {fr} image")
+            del g, o
+    finally:
+        r.close()
+        orc.close()
 
 
 def test_full_size_invariants_determinism_and_band_equivalence():

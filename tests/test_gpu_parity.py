@@ -203,8 +203,8 @@ def test_error_paths(renderer):
 
 
 def test_light_table_dirty_tracking(renderer, oracle_factory):
-    """romis_upload_lights every frame (as the drop-in does): an unchanged table is a no-op, a shorter table drops the
-    history (it stores light indices), after which the frame equals the oracle's history-free frame."""
+    """romis_upload_lights every frame (as the drop-in does): an unchanged table is a no-op; a shorter table keeps the history
+    (the reference's reservoirs hold their samples by value, reservoir.h:18-26 -- tests/test_gpu_light_edits.py has the rest)."""
     scene = load_scene("CornellNightClub")
     feat = Features(spatialResamplingPasses=1)
     W, H = 48, 32
@@ -218,7 +218,7 @@ def test_light_table_dirty_tracking(renderer, oracle_factory):
         assert_bits_equal(gimg, oimg, f"frame {fr}")
     fewer = scene.lights[:100].copy()
     renderer.upload_lights(fewer); orc.upload_lights(fewer)
-    oimg = orc.render_frame(feat, cam, W, H, False, 8, 2)         # the reference would keep stale samples; we restart
+    oimg = orc.render_frame(feat, cam, W, H, True, 8, 2)          # history samples of the removed lights live on
     gimg = renderer.render_frame(feat, cam, W, H, True, 8, 2)
     assert_bits_equal(gimg, oimg, "frame after the light table shrank")
     compare_stage("lights", "after shrink", renderer.reservoirs(abi.ROMIS_PASS_FINAL), orc.reservoirs(abi.ROMIS_PASS_FINAL))

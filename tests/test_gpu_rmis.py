@@ -57,6 +57,29 @@ def test_rmis_larger_frame_many_lights(renderer, oracle_factory):
         assert_bits_equal(gimg, oimg, f"strategy {strategy} image")
 
 
+def test_rmis_no_neighbours(renderer, oracle_factory):
+    """numNeighboursToSample = 0 (the reference's UI allows it, ui.cpp:307): random and similar strategies resample nothing but
+    the pixel itself; EqualSimilarDissimilar is rejected (its unsigned count wraps in the reference and takes the whole window,
+    neighbour_selection.cpp:95-98 -- the k + 1 planes of the grid cannot hold that)."""
+    from romis_b200.api import RomisError
+    scene = load_scene("CornellNightClub"); W, H = 40, 24
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    orc = oracle_factory(); orc.upload_scene(scene); renderer.upload_scene(scene)
+    feat = Features(numNeighboursToSample=0, initialSamplesVisibilityCheck=True)
+    for strategy in (abi.ROMIS_NEIGHBOURS_RANDOM, abi.ROMIS_NEIGHBOURS_SIMILAR):
+        for weights in (abi.ROMIS_MIS_EQUAL, abi.ROMIS_MIS_BALANCE):
+            rp = RmisParams(maxIterationsMIS=2, misWeightRMIS=weights, neighbourSelectionStrategy=strategy)
+            oimg, oxy, ocnt = orc.render_frame_rmis(feat, rp, cam, W, H, 12, 0)
+            gimg = renderer.render_frame_rmis(feat, rp, cam, W, H, 12, 0)
+            gxy, gcnt = renderer.rmis_neighbours()
+            assert (gcnt == 1).all()
+            assert_bits_equal(gcnt, ocnt, f"k=0 strategy {strategy} count"); assert_bits_equal(gxy, oxy, f"k=0 strategy {strategy} grid")
+            assert_bits_equal(gimg, oimg, f"k=0 strategy {strategy} weights {weights} image")
+    for render in (renderer.render_frame_rmis, renderer.render_frame_romis):
+        with pytest.raises(RomisError, match="EqualSimilarDissimilar"):
+            render(feat, RmisParams(neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_EQUAL_SIMILAR_DISSIMILAR), cam, W, H, 12, 0)
+
+
 def test_rmis_leaves_restir_history_alone(renderer, oracle_factory):
     """An R-MIS frame between two ReSTIR frames must not disturb the temporal history (it works in a scratch buffer)."""
     scene = load_scene("CornellNightClub"); W, H = 48, 32

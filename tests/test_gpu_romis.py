@@ -8,7 +8,7 @@ import pytest
 from romis_b200 import abi
 from romis_b200.scene import Features, RmisParams, synthetic_lights
 from cases import NIGHTCLUB_CAM, ROMIS_CASES
-from common import assert_bits_equal, assert_solve_tolerance, camera_from_array, load_golden, load_scene
+from common import assert_bits_equal, assert_image_rmse, assert_solve_tolerance, camera_from_array, load_golden, load_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,7 @@ def test_romis_gpu_matches_oracle_and_golden(case, renderer, oracle_factory):
     assert_bits_equal(gB, g["contributions"], f"{case} contribution vectors vs reference")
     assert_bits_equal(gimg, oimg, f"{case} image vs oracle")
     assert_solve_tolerance(gimg, g["image"], f"{case} image vs reference")
+    assert_image_rmse(gimg, g["image"], 1e-3, f"{case} image vs reference (north_star: RMSE <= 1e-3)")
 
 
 def test_romis_larger_frame_many_lights(renderer, oracle_factory):

@@ -19,7 +19,7 @@ from oracle import pyoracle
 from romis_b200 import abi
 from romis_b200.scene import Features, RmisParams
 from cases import CORNELL_CAM, NIGHTCLUB_CAM, ROMIS_CASES
-from common import assert_bits_equal, assert_solve_tolerance, camera_from_array, load_golden, load_scene
+from common import assert_bits_equal, assert_image_rmse, assert_solve_tolerance, camera_from_array, load_golden, load_scene
 
 
 @pytest.mark.parametrize("case", sorted(ROMIS_CASES))
@@ -31,6 +31,7 @@ def test_romis_oracle_matches_reference_golden(case, oracle_factory):
     assert_bits_equal(A, g["matrices"], f"{case} technique matrices")
     assert_bits_equal(B, g["contributions"], f"{case} contribution vectors")
     assert_solve_tolerance(img, g["image"], f"{case} image")
+    assert_image_rmse(img, g["image"], 1e-3, f"{case} image vs reference (north_star: RMSE <= 1e-3)")
 
 
 def test_cod_solver_against_float64_least_squares(oracle_factory):
@@ -77,3 +78,4 @@ def test_romis_restatement_equals_compiled_reference(oracle_factory, strategy):
         oi, oA, oB = orc.render_frame_romis(feat, rp, rcam, W, H, 4321 + k, 1)
         assert_bits_equal(oA, rA, f"k={k} technique matrices"); assert_bits_equal(oB, rB, f"k={k} contribution vectors")
         assert_solve_tolerance(oi, ri, f"k={k} image")
+        assert_image_rmse(oi, ri, 1e-3, f"k={k} image (RMSE)")

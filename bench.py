@@ -12,17 +12,20 @@ Frame 0 has no temporal history, so warm-up frames establish it; every timed fra
                 similarity-based neighbours; R-MIS with equal weights, R-OMIS direct estimator).  One GPU.
 
   value  frames/s with everything resident in HBM, device time (CUDA events on the launching stream), image left
-         on the device.  For N > 1 the frame is split into N row bands, one process per GPU, reservoir halo rows
-         exchanged over NCCL before each spatial pass; time = max over ranks; "scaling": "strong" (one frame).
+         on the device.  For N > 1 the frame is split into N row bands, one process per GPU; before each spatial pass the
+         boundary reservoir rows are pushed into the neighbouring bands' halo rows over NVLink (peer-mapped CUDA-IPC
+         memory, flag-ordered; NCCL only bootstraps -- `--halo nccl` selects NCCL send/recv instead); time = max over
+         ranks; "scaling": "strong" (one frame).
   e2e    the same metric through the reference-facing call romis_render_frame with HOST buffers: per step the
-         scene's lights are handed over again (the reference reads scene.lights fresh every frame, light.cpp:46-66) with
-         one light edited, so the table is dirty and is re-packed and re-sent, and the float RGB image is read back into
-         pinned host memory, all inside the timed region.
+         scene's lights are handed over again (the reference reads scene.lights fresh every frame, light.cpp:46-66;
+         the whole table is compared with what the device holds) and the float RGB image is read back into page-locked
+         host memory, all inside the timed region.  `e2e.light_edit` is the same with one light edited per frame (its
+         old record is archived for the history samples drawn from it, tests/test_gpu_light_edits.py).
   roofline / cpu_baseline: see DESIGN.md "measurement".
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/libromis_ref.so: the reference's
-translation units compiled here, OpenMP on all host cores, thread-safe RNG shim) on a bounded sample of the same
-workload; rank 0 only.
+translation units compiled here, OpenMP on ALL host cores set explicitly -- torchrun's OMP_NUM_THREADS=1 is ignored --,
+thread-safe RNG shim) on full-size frames of the same workload; rank 0 only.
 """
 from __future__ import annotations
 
@@ -87,42 +90,59 @@ def pass_bytes(N: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed legs, polled through NVML every ~2 ms from a thread (nvidia-smi -lms
+    needs ~1 s to start and then misses a 12 ms region).  Only samples taken between begin() and end() count."""
 
     def __init__(self, gpu_index: int):
-        self.rows = []; self.proc = None; self.gpu = gpu_index
+        self.gpu = gpu_index; self.rows = []; self.on = False; self.stop_flag = False; self.th = None; self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:       # noqa: BLE001 -- no NVML: the line says so (samples: 0)
+            self.h = None; self.sm_max = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+        if self.h is None:
+            return
+        self.th = threading.Thread(target=self._poll, daemon=True); self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def begin(self):
+        self.on = True
+
+    def end(self):
+        self.on = False
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            if self.on:
+                try:
+                    reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons(self.h))))
+                except Exception:   # noqa: BLE001
+                    pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                pass
-        sm = []; mx = 0; reasons = set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=1)
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "NVML unavailable"}
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+        reasons = set()
+        for _, bits in self.rows:
+            for name, attr, dflt in names:
+                if bits & int(getattr(nv, attr, dflt)):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "NVML polled every ~2 ms during the timed legs (value, per-stage repeat, e2e)"}
 
 
 def measured_peak_gbs():
@@ -135,27 +155,53 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+REF_FULL_BUDGET_S = 240.0       # full-size reference frames per run: as many of the K steps as fit this budget
+
+
 def run_reference(args, label, scene, W, H, feat, cam, rank, world):
-    """The reference's own CPU path on the host cores, bounded sample = the workload at 1/4 x 1/4 resolution."""
+    """The reference's own CPU path (oracle/_ref: its translation units compiled here) on ALL host cores -- set explicitly,
+    torchrun exports OMP_NUM_THREADS=1 -- at the workload's FULL size: one step = one full frame (about 8.5 s at C2 on 16
+    cores), so steps x ms_per_step is the time this run really took.  Warm-up: reduced-size frames, then one full-size
+    frame (a resolution change drops the history, so the timed frames need a full-size predecessor).  If K full frames do
+    not fit REF_FULL_BUDGET_S the remaining steps are reduced-size samples scaled by pixel count (stated in `sample`)."""
     if rank != 0:
         return
     from oracle.pyoracle import RefLib, REF_FLAG_TIMING_RNG
     ref = RefLib()
+    cores = host_cores()
+    ref.lib.ref_set_num_threads(cores)
     ref.set_scene(scene)
     div = 4 if W * H >= 1920 * 1080 else 2
     w, h = W // div, H // div
     scale = (w * h) / float(W * H)
-    times = []
-    for fr in range(args.warmup + args.steps):
+
+    def frame(fr, ww, hh):
         t0 = time.perf_counter()
-        ref.render_frame(feat, camera_for_frame(args.config, cam, fr), w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
-        dt = time.perf_counter() - t0
-        if fr >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times)) / scale          # scaled to the full frame: cost is linear in pixels
+        ref.render_frame(feat, camera_for_frame(args.config, cam, fr), ww, hh, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+        return time.perf_counter() - t0
+    fr = 0
+    for _ in range(max(0, args.warmup - 1)):
+        frame(fr, w, h); fr += 1
+    est = frame(fr, W, H); fr += 1                          # full-size warm-up frame (no history of its size yet: slightly cheaper)
+    n_full = max(1, min(args.steps, int(REF_FULL_BUDGET_S / max(est, 1e-3))))
+    times = []
+    for _ in range(n_full):
+        times.append(frame(fr, W, H)); fr += 1
+    if n_full < args.steps:
+        frame(fr, w, h); fr += 1                            # history at the sample size
+        for _ in range(args.steps - n_full):
+            times.append(frame(fr, w, h) / scale); fr += 1
+    ms = 1e3 * float(np.mean(times))
     fps = 1e3 / ms
-    cores = ref.num_threads()
-    sample = f"{w}x{h} frames of the same scene/Features ({scale:.4f} of the pixels), time scaled by pixel count; OpenMP {cores} threads, thread-safe RNG shim"
+    sample = (f"{n_full} full {W}x{H} frames" + (f" + {args.steps - n_full} frames at {w}x{h} scaled by pixel count" if n_full < args.steps else "") +
+              f"; OpenMP {cores} threads (set explicitly), thread-safe RNG shim, harness BVH instead of Embree")
     line = {"impl": "reference", "metric": "ReSTIR frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": label, "width": W, "height": H},
@@ -165,33 +211,50 @@ def run_reference(args, label, scene, W, H, feat, cam, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(scene, W, H, feat, cam, budget_s=20.0):
-    """Reported baseline next to the GPU number: oracle/_ref (the compiled reference) when present, else the C port."""
-    div = 4 if W * H >= 1920 * 1080 else 2
-    w, h = W // div, H // div
-    scale = (w * h) / float(W * H)
+def cpu_baseline_leg(scene, W, H, feat, cam, config="c2"):
+    """Reported baseline next to the GPU number (about 25 s of CPU work): oracle/_ref (the compiled reference) when present,
+    else the C port.  One full-size frame is timed, after a full-size predecessor; the reference's own random sources
+    ("as-is": glibc rand() behind its lock, std::random_device + std::mt19937 constructed per pixel, SURVEY.md 8d (i)) are
+    timed on a 1/64-pixel sample with all cores and with one."""
+    cores = host_cores()
     try:
-        from oracle.pyoracle import RefLib, REF_FLAG_TIMING_RNG
-        ref = RefLib(); ref.set_scene(scene)
-        kind, cores = "reference", ref.num_threads()
+        from oracle.pyoracle import RefLib, REF_FLAG_TIMING_RNG, REF_FLAG_ASIS_RNG
+        ref = RefLib(); ref.lib.ref_set_num_threads(cores); ref.set_scene(scene)
+        kind = "reference"
 
-        def frame(fr):
-            ref.render_frame(feat, cam, w, h, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+        def frame(fr, ww, hh, flags=REF_FLAG_TIMING_RNG):
+            t0 = time.perf_counter()
+            ref.render_frame(feat, camera_for_frame(config, cam, fr), ww, hh, fr > 0, SEED, fr, flags, dump=False, want_image=True)
+            return time.perf_counter() - t0
     except (FileNotFoundError, OSError):
         from oracle.pyoracle import Oracle
+        ref = None
         orc = Oracle(); orc.upload_scene(scene)
-        kind, cores = "port", os.cpu_count() or 1
-        cam_abi = cam.to_abi(w, h)
+        kind = "port"
 
-        def frame(fr):
-            orc.render_frame(feat, cam_abi, w, h, fr > 0, SEED, fr)
-    frame(0)
-    times = []; t_start = time.perf_counter(); fr = 1
-    while len(times) < 5 and (time.perf_counter() - t_start) < budget_s:
-        t0 = time.perf_counter(); frame(fr); times.append(time.perf_counter() - t0); fr += 1
-    ms = 1e3 * float(np.median(times)) / scale
-    return {"value": 1e3 / ms, "unit": "frames/s", "cores": cores, "kind": kind,
-            "sample": f"{len(times)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
+        def frame(fr, ww, hh, flags=0):
+            t0 = time.perf_counter()
+            orc.render_frame(feat, camera_for_frame(config, cam, fr).to_abi(ww, hh), ww, hh, fr > 0, SEED, fr)
+            return time.perf_counter() - t0
+    frame(0, W, H)
+    t = frame(1, W, H)
+    out = {"value": 1.0 / t, "unit": "frames/s", "cores": cores, "kind": kind,
+           "sample": f"1 full {W}x{H} frame (frame 1, after a full-size frame 0), same scene/Features; " +
+                     ("OpenMP on all host cores (set explicitly), thread-safe RNG shim, harness BVH instead of Embree" if ref else "C restatement, OpenMP")}
+    if ref is not None:
+        w, h = max(16, W // 8), max(16, H // 8)
+        scale = (w * h) / float(W * H)
+        as_is = []
+        for n_thr in (cores, 1):
+            ref.lib.ref_set_num_threads(n_thr)
+            frame(0, w, h, REF_FLAG_ASIS_RNG)
+            ts = [frame(1 + i, w, h, REF_FLAG_ASIS_RNG) for i in range(2)]
+            as_is.append({"value": scale / float(np.median(ts)), "unit": "frames/s", "cores": n_thr, "kind": "reference",
+                          "rng": "as-is: glibc rand(), std::random_device + std::mt19937 per pixel",
+                          "sample": f"2 frames at {w}x{h} ({scale:.4f} of the pixels), median, scaled by pixel count"})
+        ref.lib.ref_set_num_threads(cores)
+        out["as_is"] = as_is
+    return out
 
 
 MIS_DEFAULT_STEPS = 10
@@ -233,7 +296,7 @@ def run_mis(args, mode, rank, world):
             fn(feat, rp, cam, w, h, SEED, fr, False)
             if fr >= max(1, args.warmup):
                 times.append(time.perf_counter() - t0)
-        ms = 1e3 * float(np.mean(times)) / scale; fps = 1e3 / ms; cores = os.cpu_count() or 1
+        ms = 1e3 * float(np.mean(times)) / scale; fps = 1e3 / ms; cores = host_cores()
         sample = f"{w}x{h} frames of the same scene/Features ({scale:.4f} of the pixels), time scaled by pixel count; OpenMP on all {cores} host cores, thread-safe RNG shim"
         print(json.dumps({"impl": "reference", "metric": f"{mode.upper()} frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -297,7 +360,7 @@ def run_mis(args, mode, rank, world):
         while len(ts) < 3 and time.perf_counter() - t_start < 25.0:
             t0 = time.perf_counter(); fn(feat, rp, cam, w, h, SEED, 1 + len(ts), False); ts.append(time.perf_counter() - t0)
         cms = 1e3 * float(np.median(ts)) / scale
-        line["cpu_baseline"] = {"value": 1e3 / cms, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "reference",
+        line["cpu_baseline"] = {"value": 1e3 / cms, "unit": "frames/s", "cores": host_cores(), "kind": "reference",
                                 "sample": f"{len(ts)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
     print(json.dumps(line), flush=True)
 
@@ -355,20 +418,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def run_steps(n_steps, first_frame, host_out=None, upload_lights=False, stage_timing=False):
-        """Returns (sum of per-step device ms, per-stage sums).  L2 is flushed before every step, outside the events."""
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    edit_base = float(scene.lights["c0"][0, 0]) if len(scene.lights) else 0.0
+
+    def run_steps(n_steps, first_frame, host_out=None, lights=None, stage_timing=False):
+        """Returns (sum of per-step device ms, per-stage sums).  L2 is flushed before every step, outside the events.
+        lights: None = not handed over; "same" = the unchanged table handed over every step (compared on the host);
+        "edit" = one light edited every step (as from the reference's UI)."""
         r.set_stage_timing(stage_timing)
         total = 0.0; stages = {}
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        clocks.begin()
         for i in range(n_steps):
             fr = first_frame + i
             with torch.cuda.stream(br.stream):
                 flush.fill_(i & 0xff)
                 ev0.record(br.stream)
-            if upload_lights:
-                # a light edited every frame (as from the reference's UI): the table is dirty, so it is re-packed and re-sent
-                scene.lights["c0"][0, 0] = np.float32(0.65 + 1e-4 * (fr % 7))
-                r.upload_lights(scene.lights)
+            if lights is not None:
+                if lights == "edit" and len(scene.lights):
+                    scene.lights["c0"][0, 0] = np.float32(edit_base * (1.0 + 1e-3 * (1 + fr % 7)))
+                br.upload_lights(scene.lights)
             br.render_frame(feat, camera_for_frame(args.config, cam, fr), W, H, fr > 0, SEED, fr, out=host_out)
             with torch.cuda.stream(br.stream):
                 ev1.record(br.stream)
@@ -379,15 +450,14 @@ def main():
                 for k in ("primary_ms", "initial_ms", "temporal_ms", "shade_ms"):
                     stages[k] = stages.get(k, 0.0) + getattr(t, k)
                 stages["spatial_ms"] = stages.get("spatial_ms", 0.0) + sum(t.spatial_ms[:t.n_spatial])
+                stages["exchange_ms"] = stages.get("exchange_ms", 0.0) + sum(t.exchange_ms[:t.n_spatial])
                 stages["n_spatial"] = t.n_spatial
                 stages["launches"] = t.n_launches
+        clocks.end()
         return total, stages
 
     # ---- warm-up (establishes temporal history), then the timed K steps: device-resident ----
     run_steps(args.warmup, 0)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     barrier(); wall0 = time.perf_counter()
     dev_ms, _ = run_steps(args.steps, args.warmup)
     barrier(); wall_ms = 1e3 * (time.perf_counter() - wall0)
@@ -398,17 +468,26 @@ def main():
 
     # ---- e2e: host buffers through romis_render_frame semantics ----
     pinned = PinnedImage(H, W)
-    run_steps(2, args.warmup + 2 * args.steps, host_out=pinned.array, upload_lights=True)
+    nxt = args.warmup + 2 * args.steps
+    run_steps(2, nxt, host_out=pinned.array, lights="same"); nxt += 2
     barrier()
-    e2e_ms, _ = run_steps(args.steps, args.warmup + 2 * args.steps + 2, host_out=pinned.array, upload_lights=True)
+    e2e_ms, _ = run_steps(args.steps, nxt, host_out=pinned.array, lights="same"); nxt += args.steps
     barrier()
-    clk = clocks.stop() if rank == 0 else None      # sampled over the timed region and the two repeat legs (same workload)
+    run_steps(2, nxt, host_out=pinned.array, lights="edit"); nxt += 2
+    barrier()
+    edit_ms, _ = run_steps(args.steps, nxt, host_out=pinned.array, lights="edit"); nxt += args.steps
+    barrier()
+    if len(scene.lights):
+        scene.lights["c0"][0, 0] = np.float32(edit_base)
+    clk = clocks.stop() if rank == 0 else None
 
+    exch_share = stages.get("exchange_ms", 0.0) / max(stage_ms, 1e-9)
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms, stage_ms], dtype=torch.float64, device=device)
+        t = torch.tensor([dev_ms, e2e_ms, stage_ms, edit_ms, exch_share], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, stage_ms = [float(x) for x in t.tolist()]
+        dev_ms, e2e_ms, stage_ms, edit_ms, exch_share = [float(x) for x in t.tolist()]
     if rank != 0:
+        br.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -443,12 +522,26 @@ def main():
                     per_pass[name]["algorithmic_bytes"] = int(pb[name] * px)
                     per_pass[name]["ncu_warp_inst_per_cycle_per_sm_of_4"] = round(k["warp_inst_per_cycle_per_sm"], 2)
                     traffic[name] = per_pass[name]["dram_traffic_bytes"]
+                    if k.get("thread_inst_executed"):
+                        # the limiter these passes actually sit on: instruction issue.  achieved = thread instructions of one
+                        # launch (ncu, same command) / the live CUDA-event launch time; peak = 148 SMs x 128 lanes x SM clock
+                        sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+                        peak_issue = 148 * 128 * sm_mhz * 1e6 / 1e12
+                        ach = k["thread_inst_executed"] / (per_pass[name]["ms_per_launch"] * 1e-3) / 1e12
+                        per_pass[name]["issue"] = {"bound": "issue", "achieved": round(ach, 3), "peak": round(peak_issue, 3), "unit": "T thread-inst/s",
+                                                   "frac": round(ach / peak_issue, 4), "thread_inst_per_launch": int(k["thread_inst_executed"]),
+                                                   "active_threads_per_warp_inst": round(k["thread_inst_executed"] / max(1.0, k.get("warp_inst_executed", 0.0)), 2)}
     dominant = max(per_pass, key=lambda k: per_pass[k]["ms_per_launch"] * (stages.get("n_spatial", 1) if k == "spatial" else 1))
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": per_pass[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_pass[dominant]["frac"], "traffic": traffic.get(dominant), "traffic_source": (tj.get("source") if traffic else None),
                 "peak_source": peak_src,
                 "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the pass kernels are issue-bound by the parity-exact fp32/fp64 arithmetic, see DESIGN.md",
                 "passes": per_pass}
+    if per_pass[dominant].get("issue"):
+        roofline["issue"] = dict(per_pass[dominant]["issue"], kernel=dominant + "_kernel",
+                                 note="second roofline: thread instructions per launch (ncu capture of this command) / live launch time, against 148 SM x 128 lanes x measured SM clock")
+    n_slots = r.light_archive_size()[0]
+    edit_fps = 1e3 / (edit_ms / args.steps)
     line = {"metric": "ReSTIR frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
@@ -460,14 +553,20 @@ def main():
             "gcandidates_per_s_initial_pass": (round(px * feat.initialLightSamples / (per_pass["initial"]["ms_per_launch"] * 1e-3) / 1e9, 2)
                                                if world == 1 and per_pass.get("initial", {}).get("ms_per_launch") else None),
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(6 * 16 * len(scene.lights) + 256),
-                    "d2h_bytes_per_step": int(px * 12), "gcandidates_per_s": W * H * feat.initialLightSamples * e2e_fps / 1e9},
+            # headline e2e: the costlier of the two host sequences -- one light edited per frame (its old record archived for the
+            # history, the history re-pointed, the new record sent); `static_lights`: the same table handed over and compared
+            "e2e": {"value": edit_fps, "unit": "frames/s", "h2d_bytes_per_step": int(96 + 8 + 4 * n_slots + 256),
+                    "d2h_bytes_per_step": int(px * 12 + n_slots), "gcandidates_per_s": W * H * feat.initialLightSamples * edit_fps / 1e9,
+                    "sequence": "per frame: scene.lights handed over with one light edited (romis_upload_lights: compare, archive, re-point history, send), frame, float RGB image read back to page-locked host memory",
+                    "static_lights": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 256, "d2h_bytes_per_step": int(px * 12)}},
+            "exchange_share_of_frame": (round(exch_share, 4) if world > 1 else None),
             "gpu_launches": int(launches_per_frame * args.steps),
             "clocks": clk, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(scene, W, H, feat, cam)
+        line["cpu_baseline"] = cpu_baseline_leg(scene, W, H, feat, cam, args.config)
     print(json.dumps(line), flush=True)
     pinned.free()
+    br.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -225,7 +225,7 @@ class ref_timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in "primary_ms initial_ms temporal_ms spatial_ms shade_ms total_ms grid_copy_ms".split()]
 
 
-REF_FLAG_WHOLE_FRAME, REF_FLAG_TIMING_RNG, REF_FLAG_SPLIT_SPATIAL = 1, 2, 4
+REF_FLAG_WHOLE_FRAME, REF_FLAG_TIMING_RNG, REF_FLAG_SPLIT_SPATIAL, REF_FLAG_ASIS_RNG = 1, 2, 4, 8
 # SceneType of the reference (src/scene/scene.h:18-26)
 SCENE_TYPES = {"SingleTriangle": 0, "Cube": 1, "CubeTextured": 2, "CornellBox": 3,
                "CornellBoxParallelogramLight": 4, "CornellNightClub": 5, "Monkey": 6}

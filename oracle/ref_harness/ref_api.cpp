@@ -415,13 +415,16 @@ int ref_render_frame_mis_dropin(int mode, const romis_features* f, const romis_r
     return 0;
 }
 #endif
-int ref_num_threads(void) {
+static int g_threads = 0;       // 0 = all processors
+static int timing_threads() {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return g_threads > 0 ? g_threads : omp_get_num_procs();
 #else
     return 1;
 #endif
 }
+int ref_num_threads(void) { return timing_threads(); }
+int ref_set_num_threads(int n) { g_threads = n > 0 ? n : 0; return 0; }
 
 int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
                      const romis_rng* rng, int flags, ref_frame_dump* dump, float* out_rgb, ref_timings* tm) {
@@ -429,7 +432,8 @@ int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W,
     try {
         const Features features = toFeatures(*f);
         const bool whole = (flags & REF_FLAG_WHOLE_FRAME) != 0;     // call renderReSTIR itself
-        const bool timing = (flags & REF_FLAG_TIMING_RNG) != 0;     // thread-safe non-parity RNG, OpenMP allowed
+        const bool asis = (flags & REF_FLAG_ASIS_RNG) != 0;         // the reference's own random sources (timing only)
+        const bool timing = asis || (flags & REF_FLAG_TIMING_RNG) != 0;     // thread-safe non-parity RNG, OpenMP allowed
         Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
         Screen screen(glm::ivec2(W, H), false);
         Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
@@ -438,7 +442,7 @@ int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W,
         const bool doTemporal = features.temporalReuse && g_prev;
 
         ShimState& s = g_shim;
-        s.mode = timing ? SHIM_TIMING : SHIM_PARITY;
+        s.mode = asis ? SHIM_ASIS : timing ? SHIM_TIMING : SHIM_PARITY;
         s.seed = rng->seed; s.frame = rng->frame; s.W = W; s.H = H;
         s.N = (int)features.numSamplesInReservoir; s.k = (int)features.numNeighboursToSample;
         s.stage_queue.clear(); s.stage_pos = 0; s.stage = SHIM_STAGE_NONE;
@@ -449,7 +453,7 @@ int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W,
             s.stage_queue.push_back(ROMIS_STAGE_SPATIAL0 + (int)p);                 // spatialReuse, one bar per pass
         s.stage_queue.push_back(SHIM_STAGE_NONE);                                   // final shading loop
 #ifdef _OPENMP
-        if (!timing) omp_set_num_threads(1);
+        omp_set_num_threads(timing ? timing_threads() : 1);
 #endif
         // the reference prints a banner per stage (render.cpp:32,40; render_utils.cpp:18,39,93,97,146)
         NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);

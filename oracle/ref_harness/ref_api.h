@@ -33,7 +33,8 @@ typedef struct ref_frame_dump {
 
 typedef struct ref_timings { double primary_ms, initial_ms, temporal_ms, spatial_ms, shade_ms, total_ms, grid_copy_ms; } ref_timings;
 
-enum { REF_FLAG_WHOLE_FRAME = 1, REF_FLAG_TIMING_RNG = 2, REF_FLAG_SPLIT_SPATIAL = 4 };
+enum { REF_FLAG_WHOLE_FRAME = 1, REF_FLAG_TIMING_RNG = 2, REF_FLAG_SPLIT_SPATIAL = 4,
+       REF_FLAG_ASIS_RNG = 8 /* timing with the reference's own random sources: glibc rand(), std::random_device + std::mt19937 per pixel */ };
 
 const char* ref_last_error(void);
 int ref_set_tracer_mode(int mode);
@@ -57,6 +58,8 @@ int ref_render_frame_romis(const romis_features* f, const romis_rmis_params* rp,
                            const romis_rng* rng, float* out_rgb, float* matrices, float* contributions);
 int ref_set_mis_timing(int on);
 int ref_num_threads(void);
+/* OpenMP threads of the timing runs (n <= 0: all processors); overrides OMP_NUM_THREADS, which torchrun sets to 1 */
+int ref_set_num_threads(int n);
 int ref_render_frame(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
                      const romis_rng* rng, int flags, ref_frame_dump* dump, float* out_rgb, ref_timings* tm);
 #ifdef __cplusplus

@@ -30,18 +30,26 @@
 
 extern "C" uint32_t romis_shim_engine_next(void);   // next ENGINE-stream draw for the current pixel
 extern "C" void romis_shim_engine_ctor(void);       // a std::mt19937 was constructed
+extern "C" int romis_shim_asis(void);               // "as-is" timing arm: the reference's own random sources, at their own cost
 
 namespace romis_shim {
+// As-is mode (bench.py's second cpu_baseline entry): the real std::random_device is constructed and drawn
+// and a real std::mt19937 is seeded and drawn wherever the reference does so (once per PIXEL in genCanonicalSamples,
+// light.cpp:49-50), and rand() is glibc's (shims.cpp) -- the costs the reference pays.  These lines are parsed before the
+// macros below exist, so std::random_device / std::mt19937 here are the real ones.
 struct Device {
     using result_type = unsigned int;
-    result_type operator()() { return 0u; }
+    std::optional<std::random_device> real;
+    Device() { if (romis_shim_asis()) real.emplace(); }
+    result_type operator()() { return real ? (*real)() : 0u; }
 };
 struct Engine {
     using result_type = uint32_t;
-    explicit Engine(result_type = 0u) { romis_shim_engine_ctor(); }
+    std::optional<std::mt19937> real;
+    explicit Engine(result_type seed = 0u) { if (romis_shim_asis()) real.emplace(seed); else romis_shim_engine_ctor(); }
     static constexpr result_type min() { return 0u; }
     static constexpr result_type max() { return 0xffffffffu; }
-    result_type operator()() { return romis_shim_engine_next(); }
+    result_type operator()() { return real ? (result_type)(*real)() : romis_shim_engine_next(); }
 };
 // uniform integer in [a, b]: multiply-shift mapping of ONE 32-bit draw (romis_rng.h)
 template <class I = int>

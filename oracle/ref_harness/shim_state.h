@@ -3,7 +3,7 @@
 #include <cstdint>
 #include <vector>
 
-enum ShimMode { SHIM_PARITY = 0, SHIM_TIMING = 1 };
+enum ShimMode { SHIM_PARITY = 0, SHIM_TIMING = 1, SHIM_ASIS = 2 /* the reference's own rand() / random_device / mt19937 */ };
 enum { SHIM_STAGE_NONE = -1,        // stages without draws: primary rays, final shading
        SHIM_STAGE_PRIMARY_THEN_NEIGH = -2 };   // renderRMIS: primary rays, then the neighbour index grid (no bar of its own)
 

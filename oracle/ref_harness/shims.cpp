@@ -16,6 +16,7 @@
 #include <utils/utils.h>
 
 #include <atomic>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -99,8 +100,14 @@ extern "C" uint32_t romis_shim_engine_next(void) {
     return 0;
 }
 
+extern "C" int romis_shim_asis(void) { return g_shim.mode == SHIM_ASIS; }
+
 extern "C" int rand(void) {
     ShimState& s = g_shim;
+    if (s.mode == SHIM_ASIS) {      // glibc's rand(): one process-wide state behind a lock (what the reference calls)
+        static int (*libc_rand)(void) = reinterpret_cast<int (*)(void)>(dlsym(RTLD_NEXT, "rand"));
+        return libc_rand();
+    }
     if (s.mode != SHIM_PARITY) return int(fast_next() >> 1);
     long pix; uint32_t c;
     if (per_pixel_engine_stage(s.stage)) {

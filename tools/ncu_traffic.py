@@ -24,6 +24,10 @@ for r in rows[2:]:
         continue
     kernels[name] = {"dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
                      "duration_ms": val(r, "gpu__time_duration.sum"),
-                     "warp_inst_per_cycle_per_sm": val(r, "sm__inst_executed.avg.per_cycle_elapsed", False)}
+                     "warp_inst_per_cycle_per_sm": val(r, "sm__inst_executed.avg.per_cycle_elapsed", False),
+                     "thread_inst_executed": val(r, "smsp__thread_inst_executed_per_inst_executed.ratio", False) * val(r, "smsp__inst_executed.sum", False),
+                     "warp_inst_executed": val(r, "smsp__inst_executed.sum", False),
+                     "registers_per_thread": val(r, "launch__registers_per_thread", False),
+                     "achieved_occupancy_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active", False)}
 json.dump({"source": note, "config": config, "kernels": kernels}, open(out, "w"), indent=1)
 print(json.dumps(kernels, indent=1))

@@ -198,6 +198,13 @@ extern "C" void romis_dropin_lights_dirty(int first, int count) {
     else { g.dirtyFirst = std::min(g.dirtyFirst, first); g.dirtyEnd = std::max(g.dirtyEnd, first + count); }
 }
 
+// The Screen's pixel storage stays page-locked between frames; call this before a Screen whose frames went through the GPU path
+// is destroyed or resized (the application's one Screen lives as long as its window, main.cpp:56-65: at exit).
+extern "C" void romis_dropin_release_screen(void) {
+    if (g.pinnedPtr) romis_host_unregister(g.pinnedPtr);
+    g.pinnedPtr = nullptr; g.pinnedBytes = 0;
+}
+
 // half extents of the image plane: Trackball keeps them private (trackball.h:55-56).  The maintainer either adds two
 // accessors or, as here, the caller provides them; they are tan(fovy/2) and aspect*tan(fovy/2) (trackball.cpp:26-27).
 static thread_local float g_halfW = 0.0f, g_halfH = 0.0f;

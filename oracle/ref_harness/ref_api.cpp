@@ -364,6 +364,10 @@ void renderRMIS_gpu(const Scene& scene, const Trackball& camera, const EmbreeInt
 void renderROMIS_gpu(const Scene& scene, const Trackball& camera, const EmbreeInterface& embreeInterface, Screen& screen, const Features& features);
 extern "C" void romis_dropin_set_rng(uint64_t seed, uint32_t frame);
 extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight);
+extern "C" void romis_dropin_release_screen(void);
+// the Screens of this harness live for one call (the application's lives as long as its window): the drop-in's page-lock
+// registration of Screen::pixels() must end before the vector is freed
+struct ScreenPinGuard { ~ScreenPinGuard() { romis_dropin_release_screen(); } };
 extern "C" {
 // The reference's own Scene / Trackball / Screen / Features objects driven through the GPU drop-in.
 int ref_render_frame_dropin(const romis_features* f, const ref_camera_desc* cam, int W, int H, int history_valid,
@@ -380,6 +384,7 @@ int ref_render_frame_dropin(const romis_features* f, const ref_camera_desc* cam,
         romis_dropin_set_rng(rng->seed, rng->frame);
         static std::shared_ptr<ReservoirGrid> prevGpu;
         if (!history_valid) prevGpu.reset();
+        ScreenPinGuard unpin;
         ReservoirGrid grid = renderReSTIR_gpu(prevGpu, g_scene, camera, *g_embree, screen, features);
         prevGpu = std::make_shared<ReservoirGrid>(grid);                            // main.cpp:165
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));
@@ -408,6 +413,7 @@ int ref_render_frame_mis_dropin(int mode, const romis_features* f, const romis_r
         const float halfH = std::tan(glm::radians(cam->fov_deg) / 2.0f);            // trackball.cpp:26-27
         romis_dropin_set_half_extents(window.getAspectRatio() * halfH, halfH);
         romis_dropin_set_rng(rng->seed, rng->frame);
+        ScreenPinGuard unpin;
         if (mode) renderROMIS_gpu(g_scene, camera, *g_embree, screen, features);
         else renderRMIS_gpu(g_scene, camera, *g_embree, screen, features);
         if (out_rgb) std::memcpy(out_rgb, screen.pixels().data(), size_t(W) * H * 3 * sizeof(float));

@@ -10,10 +10,8 @@ namespace romis {
 // ES: enableShading is known to be on (the reference's default): the flag and the material's kd, which only the unshaded
 // path reads, stop occupying registers in a kernel that is short of them (measured: -3.5 %).  !ES reads the flag at run time.
 template <int NT, bool UNBIASED, bool ES>
-__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
-    int x, y; thread_pixel<true>(x, y);
-    y += fr.y0;
-    if (x >= fr.W || y >= fr.y1) return;
+__device__ __forceinline__ void spatial_pixel(const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const ResBuf& out, int pass,
+                                              int x, int y, const HaloDev* hd) {
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = ES || fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
@@ -93,6 +91,74 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
         }
     }
     res_store(out, lrow, x, r, N);
+    if (hd && hd->push) {
+        // this pixel's row is a boundary row of the band: the neighbouring band reads it as a halo row in the next pass
+        // (record and M only: the stored pdf is read for a band's own pixels alone)
+        _Pragma("unroll") for (int e = 0; e < 2; e++) {
+            if (!hd->peer_out[e] || !(e == 0 ? y < fr.y0 + hd->r : y >= fr.y1 - hd->r)) continue;
+            ResBuf pb; pb.base = hd->peer_out[e]; pb.row_stride = hd->peer_stride[e]; pb.W = out.W; pb.N = out.N;
+            const int prow = y - hd->peer_ey0[e];
+            ROMIS_FOR_SUB(j, NT, N) {
+                res_rec(pb, prow, j)[x] = make_uint4(r.light[j], __float_as_uint(r.u[j]), __float_as_uint(r.v[j]), __float_as_uint(r.W[j]));
+                res_m(pb, prow, j)[x] = r.M[j];
+            }
+        }
+    }
+}
+
+template <int NT, bool UNBIASED, bool ES>
+__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
+    int x, y; thread_pixel<true>(x, y);
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
+    spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, nullptr);
+}
+
+// The same pass for a band with peer-mapped neighbours (fused halo exchange).  Row groups next to a band edge are launched
+// first: each waits until the neighbour's token of the PREVIOUS stage has arrived (its boundary rows are in my halo, and it has
+// finished reading the halo rows of the buffer I am about to write into), runs, stores its rows twice (here and into the
+// neighbour's halo) and the last such block of an edge publishes this stage's token.  Interior row groups never wait.
+__device__ __forceinline__ void halo_spin(const uint32_t* f, uint32_t token, uint32_t* err) {
+    const volatile uint32_t* vf = f;
+    const long long t0 = clock64();
+    while ((int32_t)(*vf - token) < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }
+    }
+}
+template <int NT, bool UNBIASED, bool ES>
+__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass, HaloDev hd) {
+    int by = (int)blockIdx.y;
+    if (by >= hd.nl) by = by < hd.nl + hd.nh ? hd.gh0 + (by - hd.nl) : hd.nl + (by - hd.nl - hd.nh);
+    const int gy0 = fr.y0 + by * (int)blockDim.y, gy1 = gy0 + (int)blockDim.y;
+    const bool edge0 = hd.wait_flag[0] != nullptr && gy0 < fr.y0 + hd.r;
+    const bool edge1 = hd.wait_flag[1] != nullptr && gy1 > fr.y1 - hd.r;
+    if (edge0 || edge1) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (edge0) halo_spin(hd.wait_flag[0], hd.wait_token, hd.err);
+            if (edge1) halo_spin(hd.wait_flag[1], hd.wait_token, hd.err);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    int x, y; thread_pixel<true>(x, y, by);
+    y += fr.y0;
+    if (x < fr.W && y < fr.y1) spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, &hd);
+    if (edge0 || edge1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            _Pragma("unroll") for (int e = 0; e < 2; e++) {
+                if (!(e == 0 ? edge0 : edge1)) continue;
+                if (atomicAdd(&hd.counter[e], 1u) == hd.edge_blocks[e] - 1u) {
+                    hd.counter[e] = 0u;
+                    __threadfence_system();
+                    *(volatile uint32_t*)hd.sig_flag[e] = hd.token;
+                    __threadfence_system();
+                }
+            }
+        }
+    }
 }
 
 
@@ -103,5 +169,14 @@ void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased,
     else if (unbiased) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, true, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
     else if (es) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, false, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
     else { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, false, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
+}
+
+void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd) {
+    const bool es = fr.f.enableShading != 0;
+    if (unbiased && es) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, true, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
+    else if (unbiased) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, true, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
+    else if (es) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, false, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
+    else { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, false, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
 }
 }  // namespace romis

@@ -10,6 +10,8 @@ void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDe
                      const ResBuf& cur, const ResBuf& prev, const ResBuf& out);
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                     const ResBuf& in, const ResBuf& out, int pass);
+void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
+                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd);
 void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb);
 void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g);
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm);

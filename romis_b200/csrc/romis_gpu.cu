@@ -76,7 +76,7 @@ struct romis_ctx {
         size_t row_stride = 0;
     } peer[2];                          // [0] = band below (smaller y), [1] = band above
     DevBuf flags;                       // my flag words: {ready_from_low, ready_from_high, done_from_low, done_from_high, error}
-    uint32_t pass_token = 0, frame_token = 0;
+    uint32_t epoch = 0;                 // stage tokens: a running count of exchange stages, the same on every band
     bool exported = false;
 
     // R-MIS (romis_render_frame_rmis): neighbour grid and accumulator of the last frame
@@ -672,13 +672,18 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
 }
 
 // ------------------------------------------------------------------------------------------------
-// peer-mapped halos: the boundary rows of the buffer the next spatial pass reads are pushed straight into the
-// neighbouring bands' halo rows over NVLink (IPC-mapped device memory), ordered by flag words: no NCCL, no host sync.
-//   ready flags  token = running count of spatial passes: "my rows for this pass are in your halo"
-//   done flags   token = running count of frames:         "I finished the frame's last pass, your rows in my halo are free"
-// RAW: a pass waits for both neighbours' ready token.  WAR: the buffer a pass p >= 1 pushes into was last read by the
-// neighbour's pass p-2, which completed before it sent ready(p-1) -- already waited for; for pass 0 the last reader may be
-// the previous frame's final pass, hence the done flags.
+// peer-mapped halos ("fused halo exchange"): the boundary rows a spatial pass writes are stored twice by the pass itself --
+// into this band's buffer and, over NVLink, into the neighbouring bands' halo rows of the same buffer (IPC- or peer-mapped
+// device memory) -- and the passes are ordered by stage tokens in device memory: no NCCL call, no host synchronisation, no
+// separate copy kernel except for the rows of stage 0 (the temporal pass's output).
+//   stage    0 = the push of the first pass's input, k = spatial pass k-1; a running count over the frames (`epoch`)
+//   token    band A publishes token(s) into both neighbours' flag words once all its row groups next to that edge have
+//            finished stage s
+//   RAW      the row groups of stage s next to an edge wait for the neighbour's token(s-1): its rows are in my halo
+//   WAR      stage s writes into the neighbour's halo of buffer B_s = B_(s-2); the neighbour last read that halo in ITS
+//            stage s-1, whose edge row groups had finished when it published token(s-1) -- the same wait.  Stage 0 of a frame
+//            waits for the last token of the previous frame for the same reason.
+// Only row groups within `radius` rows of an edge ever wait; they run first, the interior of the band follows without a wait.
 // ------------------------------------------------------------------------------------------------
 struct PeerBlob {
     uint32_t magic;
@@ -689,10 +694,14 @@ struct PeerBlob {
 };
 static_assert(sizeof(PeerBlob) <= ROMIS_PEER_BLOB_BYTES, "peer blob fits the ABI buffer");
 
-static int peer_exchange(romis_ctx* c, int in, int pass) {
+// Stage 0 of a frame's exchange: the rows the first spatial pass needs come from the temporal (or initial) pass, which knows
+// nothing of neighbours, so ONE small copy kernel pushes them; it waits only for the neighbours' last token of the previous
+// frame (their halo rows of this buffer are free) and publishes this stage's token -- it does not wait for the neighbours'
+// rows, the boundary blocks of the pass do.
+static int peer_push_stage0(romis_ctx* c, int in) {
     const int r = (int)c->fr.f.spatialResampleRadius;
-    uint32_t* my = (uint32_t*)c->flags.p;      // {ready_from_low, ready_from_high, done_from_low, done_from_high, error, ticket}
-    c->pass_token++;
+    uint32_t* my = (uint32_t*)c->flags.p;      // {token_from_low, token_from_high, -, -, error, ticket, edge counter low, edge counter high}
+    const uint32_t wait = c->epoch, token = ++c->epoch;
     const unsigned char* src = (const unsigned char*)c->res[in].p;
     const romis_ctx::Peer& lo = c->peer[0]; const romis_ctx::Peer& hi = c->peer[1];
     const size_t bytes = (size_t)r * c->row_stride;     // row_stride is a multiple of 16
@@ -700,11 +709,39 @@ static int peer_exchange(romis_ctx* c, int in, int pass) {
     launch_halo_push(c->stream,
                      lo.on ? src + (size_t)(c->y0 - c->ey0) * c->row_stride : nullptr, lo.on ? lo.res[in] + (size_t)(c->y0 - lo.ey0) * lo.row_stride : nullptr, lo.on ? bytes : 0,
                      hi.on ? src + (size_t)(c->y1 - r - c->ey0) * c->row_stride : nullptr, hi.on ? hi.res[in] + (size_t)(c->y1 - r - hi.ey0) * hi.row_stride : nullptr, hi.on ? bytes : 0,
-                     (pass == 0 && lo.on) ? my + 2 : nullptr, (pass == 0 && hi.on) ? my + 3 : nullptr, c->frame_token,
-                     lo.on ? lo.flags + 1 : nullptr, hi.on ? hi.flags + 0 : nullptr, c->pass_token,
-                     lo.on ? my + 0 : nullptr, hi.on ? my + 1 : nullptr, my + 4, (unsigned int*)(my + 5));
+                     lo.on ? my + 0 : nullptr, hi.on ? my + 1 : nullptr, wait,
+                     lo.on ? lo.flags + 1 : nullptr, hi.on ? hi.flags + 0 : nullptr, token,
+                     nullptr, nullptr, my + 4, (unsigned int*)(my + 5));
     RCHECK(c, cudaGetLastError());
     return ROMIS_OK;
+}
+
+// Fused halo exchange of spatial pass `pass` (HaloDev, k_spatial.cu spatial_halo_kernel): stage tokens are a running count
+// over the frames, identical on every band because all bands issue the same sequence of stages.
+static HaloDev halo_for_pass(romis_ctx* c, int out, int pass, const dim3& grid, const dim3& block) {
+    HaloDev hd; std::memset(&hd, 0, sizeof hd);
+    uint32_t* my = (uint32_t*)c->flags.p;
+    const int r = (int)c->fr.f.spatialResampleRadius, rows = c->y1 - c->y0, bh = (int)block.y, nby = (int)grid.y;
+    const bool last = pass + 1 == (int)c->fr.f.spatialResamplingPasses;
+    const int nlo = std::min(nby, (r + bh - 1) / bh), gh0 = std::max(0, (rows - r) / bh);
+    for (int e = 0; e < 2; e++) {
+        const romis_ctx::Peer& p = c->peer[e];
+        if (!p.on) continue;
+        hd.peer_out[e] = last ? nullptr : p.res[out];
+        hd.peer_stride[e] = p.row_stride; hd.peer_ey0[e] = p.ey0;
+        hd.wait_flag[e] = my + e;
+        hd.sig_flag[e] = p.flags + (e == 0 ? 1 : 0);
+        hd.edge_blocks[e] = (unsigned int)((e == 0 ? nlo : nby - gh0) * (int)grid.x);
+    }
+    hd.counter = (unsigned int*)(my + 6);
+    hd.err = my + 4;
+    hd.wait_token = c->epoch; hd.token = ++c->epoch;
+    hd.nl = c->peer[0].on ? nlo : 0;
+    hd.gh0 = std::max(gh0, hd.nl);
+    hd.nh = c->peer[1].on ? nby - hd.gh0 : 0;
+    hd.push = last ? 0 : 1;
+    hd.r = r;
+    return hd;
 }
 
 // Per-row count of pixels whose primary ray hits geometry, for the whole frame: most of the work of every pass sits in
@@ -749,7 +786,7 @@ extern "C" int romis_band_prepare(romis_ctx* c, const romis_features* f, int W, 
     RCHECK(c, c->flags.ensure(8 * sizeof(uint32_t)));
     RCHECK(c, cudaMemsetAsync(c->flags.p, 0, 8 * sizeof(uint32_t), c->stream));
     RCHECK(c, cudaStreamSynchronize(c->stream));
-    c->pass_token = 0; c->frame_token = 0;
+    c->epoch = 0;
     return ROMIS_OK;
 }
 
@@ -831,8 +868,12 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     // ping-pong between the two work buffers; the history buffer is never written during a frame
     const int in = c->cur, out = c->spare;
     const dim3 gOwn = grid_for(c->W, c->y1 - c->y0);
-    if (c->peer[0].on || c->peer[1].on) { int prc = peer_exchange(c, in, pass); if (prc) return prc; c->n_launches++; RCHECK(c, mark(c, 6, pass)); }
-    launch_spatial(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass);
+    if (c->peer[0].on || c->peer[1].on) {
+        if (pass == 0) { int prc = peer_push_stage0(c, in); if (prc) return prc; c->n_launches++; RCHECK(c, mark(c, 6, pass)); }
+        const HaloDev hd = halo_for_pass(c, out, pass, gOwn, kBlock);
+        launch_spatial_halo(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass, hd);
+    } else
+        launch_spatial(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass);
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 4, pass));
@@ -841,13 +882,6 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     c->spare = in;
     c->cur = out;
     c->next_pass++;
-    if ((c->peer[0].on || c->peer[1].on) && pass + 1 == (int)c->fr.f.spatialResamplingPasses) {
-        // last pass of the frame: tell the neighbours that their rows in my halo regions are no longer being read
-        c->frame_token++;
-        launch_signal(c->stream, c->peer[0].on ? c->peer[0].flags + 3 : nullptr, c->frame_token,
-                      c->peer[1].on ? c->peer[1].flags + 2 : nullptr, c->frame_token);
-        RCHECK(c, cudaGetLastError());
-    }
     return ROMIS_OK;
 }
 

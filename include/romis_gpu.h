@@ -8,7 +8,7 @@
  * stands in for.  Plain pointers and sizes only, no C++ or torch types, no exceptions: every call
  * returns ROMIS_OK (0) or a negative romis_status and leaves a message in romis_last_error().
  *
- * A context is bound to ONE CUDA device and is not re-entrant (the reference's CLI mode calls
+ * A context is bound to ONE CUDA device (or, created with several device ids, to one row band per device) and is not re-entrant (the reference's CLI mode calls
  * renderRayTraced from one thread per camera, main.cpp:213-230: create one context per thread).
  * There is no CPU fallback: romis_create fails when no CUDA device is usable.
  */
@@ -128,9 +128,14 @@ typedef struct romis_rng {
 } romis_rng;
 
 /* ---- lifetime ---- */
-/* device_ids/n_devices: exactly one device per context (multi-GPU = one context per GPU, each
- * owning a row band, see romis_set_band).  Replaces: EmbreeInterface construction + the implicit
- * process state of the reference (main.cpp:56-65). */
+/* device_ids / n_devices: n_devices == 1 (or 0 with a NULL list: device 0) binds the context to one GPU.
+ * n_devices > 1 makes a MULTI-DEVICE context for the reference's actual caller -- one thread of one process (main.cpp:164,
+ * ui.cpp:161): the frame is cut into one row band per device (equal cost from the per-row hit profile), the bands' boundary
+ * reservoir rows travel between neighbouring devices over NVLink inside the spatial pass (cudaDeviceEnablePeerAccess), and
+ * romis_render_frame fills the caller's single out_rgb.  Results are bit-identical to the one-device frame.  On a multi-device
+ * context the per-device calls (stepwise frames, bands, peer_*, R-MIS / R-OMIS frames, render_frame_device) return
+ * ROMIS_ERR_INVALID; the same device may be listed twice (two bands on one GPU: a test configuration).
+ * Replaces: EmbreeInterface construction + the implicit process state of the reference (main.cpp:56-65). */
 int romis_create(const int* device_ids, int n_devices, romis_ctx** out);
 void romis_destroy(romis_ctx* ctx);
 /* Last error text of `ctx`; ctx == NULL returns the last romis_create failure. */

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -39,6 +40,8 @@ struct GpuState {
     romis_ctx* ctx = nullptr;
     const void* sceneKey = nullptr;     // identity of the uploaded geometry
     uint64_t sceneSig = 0;
+    bool multi = false;                 // several GPUs (ROMIS_DEVICES): R-MIS / R-OMIS frames use a one-device context of their own
+    romis_ctx* misCtx = nullptr; uint64_t misSig = 0; int misDevice = 0;
     bool sceneDirty = true;             // romis_dropin_invalidate_scene (hook next to EmbreeInterface::changeScene)
     uint64_t seed = 0x524f4d4953ull;    // "ROMIS"
     uint32_t frame = 0;
@@ -51,6 +54,7 @@ struct GpuState {
     void* pinnedPtr = nullptr; size_t pinnedBytes = 0;
     ~GpuState() {
         if (pinnedPtr) romis_host_unregister(pinnedPtr);
+        if (misCtx) romis_destroy(misCtx);
         if (ctx) romis_destroy(ctx);
     }
 };
@@ -87,7 +91,7 @@ uint64_t geometrySignature(const Scene& scene) {
     return h;
 }
 
-void uploadScene(const Scene& scene) {
+void uploadScene(romis_ctx* ctx, const Scene& scene) {
     std::vector<romis_mesh_desc> descs(scene.meshes.size());
     std::vector<std::vector<uint32_t>> tris(scene.meshes.size());
     std::vector<const Image*> images;
@@ -116,7 +120,7 @@ void uploadScene(const Scene& scene) {
         }
     }
     for (size_t k = 0; k < images.size(); k++) textures.push_back(romis_texture { pixels[k].data(), images[k]->width, images[k]->height });
-    check(romis_upload_scene(g.ctx, descs.data(), (int)descs.size(), textures.data(), (int)textures.size()), "romis_upload_scene");
+    check(romis_upload_scene(ctx, descs.data(), (int)descs.size(), textures.data(), (int)textures.size()), "romis_upload_scene");
 }
 
 romis_light toPod(const std::variant<PointLight, SegmentLight, ParallelogramLight>& v) {
@@ -213,13 +217,19 @@ extern "C" void romis_dropin_set_half_extents(float halfWidth, float halfHeight)
 // Context, scene / light upload and camera, common to the three entry points
 static romis_camera prepare(const Scene& scene, const Trackball& camera) {
     if (!g.ctx) {
-        int dev = 0;
-        if (romis_create(&dev, 1, &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
+        // ROMIS_DEVICES=0,1,2,3 in the environment: one row band per listed GPU, all driven from this thread; default: GPU 0
+        std::vector<int> devs;
+        if (const char* e = std::getenv("ROMIS_DEVICES")) {
+            for (const char* p = e; *p;) { char* end; long v = std::strtol(p, &end, 10); if (end == p) break; devs.push_back((int)v); p = *end ? end + 1 : end; }
+        }
+        if (devs.empty()) devs.push_back(0);
+        if (romis_create(devs.data(), (int)devs.size(), &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
+        g.multi = devs.size() > 1; g.misDevice = devs[0];
     }
     // EmbreeInterface::changeScene (embree_interface.cpp:53-56) has no notification we could hook: detect geometry changes
     const uint64_t sig = geometrySignature(scene);
     if (g.sceneDirty || g.sceneKey != scene.meshes.data() || g.sceneSig != sig) {
-        uploadScene(scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; g.sceneDirty = false;
+        uploadScene(g.ctx, scene); g.sceneKey = scene.meshes.data(); g.sceneSig = sig; g.sceneDirty = false;
     }
     uploadLights(scene);
     romis_camera cam;
@@ -230,6 +240,18 @@ static romis_camera prepare(const Scene& scene, const Trackball& camera) {
     cam.half_width = g_halfW; cam.half_height = g_halfH;
     if (g_halfH == 0.0f) throw std::runtime_error("romis drop-in: image-plane half extents not set (romis_dropin_set_half_extents)");
     return cam;
+}
+
+// R-MIS / R-OMIS frames are not sharded: with several GPUs configured they run on a one-device context of their own
+static romis_ctx* misContext(const Scene& scene) {
+    if (!g.multi) return g.ctx;
+    if (!g.misCtx && romis_create(&g.misDevice, 1, &g.misCtx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
+    const uint64_t sig = geometrySignature(scene);
+    if (g.misSig != sig) { uploadScene(g.misCtx, scene); g.misSig = sig; }
+    std::vector<romis_light> lights(scene.lights.size());
+    for (size_t i = 0; i < lights.size(); i++) lights[i] = toPod(scene.lights[i]);
+    if (romis_upload_lights(g.misCtx, lights.data(), (int)lights.size()) != ROMIS_OK) throw std::runtime_error(std::string("romis_upload_lights: ") + romis_last_error(g.misCtx));
+    return g.misCtx;
 }
 
 ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid,
@@ -277,7 +299,9 @@ void ROMIS_DROPIN_RMIS_NAME(const Scene& scene, const Trackball& camera, const E
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    check(romis_render_frame_rmis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)), "romis_render_frame_rmis");
+    romis_ctx* ctx = misContext(scene);
+    if (romis_render_frame_rmis(ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)) != ROMIS_OK)
+        throw std::runtime_error(std::string("romis_render_frame_rmis: ") + romis_last_error(ctx));
 }
 
 // saveAlphasVisualisation (render.cpp:227-229, BMP dumps of the per-technique alphas) is a debugging aid of the CPU path
@@ -288,5 +312,7 @@ void ROMIS_DROPIN_ROMIS_NAME(const Scene& scene, const Trackball& camera, const 
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    check(romis_render_frame_romis(g.ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)), "romis_render_frame_romis");
+    romis_ctx* ctx = misContext(scene);
+    if (romis_render_frame_romis(ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)) != ROMIS_OK)
+        throw std::runtime_error(std::string("romis_render_frame_romis: ") + romis_last_error(ctx));
 }

@@ -150,13 +150,15 @@ class PinnedImage:
 
 
 class RestirRenderer:
-    """One context = one GPU (optionally one row band of the frame)."""
+    """One context = one GPU (optionally one row band of the frame); with a list of devices: one context driving one row band
+    per GPU from this single process (romis_create with n_devices > 1)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.lib = load_library()
         ctx = C.c_void_p()
-        dev = (C.c_int * 1)(device)
-        rc = self.lib.romis_create(dev, 1, C.byref(ctx))
+        devices = list(device) if isinstance(device, (list, tuple)) else [int(device)]
+        dev = (C.c_int * len(devices))(*devices)
+        rc = self.lib.romis_create(dev, len(devices), C.byref(ctx))
         if rc != 0:
             raise RomisError(f"romis_create failed ({rc}): {self.lib.romis_last_error(None).decode()}")
         self.ctx = ctx

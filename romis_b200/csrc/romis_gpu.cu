@@ -68,8 +68,14 @@ struct romis_ctx {
     int n_launches = 0;
 
     // peer-mapped halos (one process per GPU; see romis_peer_attach)
+    // multi-device context (romis_create with n_devices > 1): one child context per device, each renders a row band of the
+    // frame; the parent only holds the children, the band edges and the error text (see "multi-device context" below)
+    std::vector<romis_ctx*> kids;
+    std::vector<int> g_edges; int g_active = 0, g_W = 0, g_H = 0, g_N = 0, g_halo = -1; bool g_wired = false;
+
     struct Peer {
         bool on = false;
+        bool ipc = false;                                       // mapped through cudaIpcOpenMemHandle (another process)
         unsigned char* res[3] = {nullptr, nullptr, nullptr};   // the neighbour's three reservoir buffers, IPC-mapped
         uint32_t* flags = nullptr;                              // the neighbour's flag words, IPC-mapped
         int y0 = 0, y1 = 0, ey0 = 0, ey1 = 0;
@@ -120,6 +126,16 @@ struct romis_ctx {
     } while (0)
 
 static int fail(romis_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+// multi-device context (defined after the frame functions)
+static int group_create(const int* device_ids, int n, romis_ctx** out, std::string& err);
+static int group_upload_scene(romis_ctx* g, const romis_mesh_desc* meshes, int n_meshes, const romis_texture* textures, int n_textures);
+static int group_upload_lights(romis_ctx* g, const romis_light* lights, int n, int first, int count);
+static int group_render_frame(romis_ctx* g, const romis_features* f, const romis_camera* cam, int W, int H, int history_valid, const romis_rng* rng, float* out_rgb);
+static int group_timings(romis_ctx* g, romis_timings* out);
+static int group_fail(romis_ctx* g, romis_ctx* kid, int rc);
+#define ROMIS_GROUP_EACH(g, CALL) do { for (romis_ctx* k : (g)->kids) { int rc__ = (CALL); if (rc__) return group_fail((g), k, rc__); } return ROMIS_OK; } while (0)
+#define ROMIS_GROUP_ACTIVE(g, CALL) do { for (int i__ = 0; i__ < std::max(1, (g)->g_active); i__++) { romis_ctx* k = (g)->kids[i__]; int rc__ = (CALL); if (rc__) return group_fail((g), k, rc__); } return ROMIS_OK; } while (0)
+#define ROMIS_NOT_ON_GROUP(c, what) if ((c) && !(c)->kids.empty()) return fail((c), ROMIS_ERR_INVALID, what ": per-device call, not available on a multi-device context")
 static float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 static ResBuf resbuf(const romis_ctx* c, int i) {
@@ -144,10 +160,13 @@ extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** ou
     auto set_err = [](const std::string& s) { std::lock_guard<std::mutex> lk(g_err_mutex); g_create_err = s; };
     if (!out) { set_err("out == NULL"); return ROMIS_ERR_INVALID; }
     *out = nullptr;
-    if (n_devices != 1 && !(n_devices == 0 && device_ids == nullptr)) {
-        set_err("one context drives exactly one device; create one context per GPU and give each a row band (romis_set_band)");
-        return ROMIS_ERR_INVALID;
+    if (n_devices > 1 && device_ids) {           // one caller, several GPUs: a parent context with one row band per device
+        std::string err;
+        int rc = group_create(device_ids, n_devices, out, err);
+        if (rc != ROMIS_OK) set_err(err);
+        return rc;
     }
+    if (n_devices != 1 && !(n_devices == 0 && device_ids == nullptr)) { set_err("romis_create: bad device list"); return ROMIS_ERR_INVALID; }
     int dev = (n_devices == 1 && device_ids) ? device_ids[0] : 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -176,6 +195,12 @@ extern "C" int romis_create(const int* device_ids, int n_devices, romis_ctx** ou
 extern "C" int romis_peer_detach(romis_ctx* c);
 extern "C" void romis_destroy(romis_ctx* c) {
     if (!c) return;
+    if (!c->kids.empty()) {
+        for (romis_ctx* k : c->kids) { cudaSetDevice(k->device); if (k->stream) cudaStreamSynchronize(k->stream); k->peer[0] = romis_ctx::Peer(); k->peer[1] = romis_ctx::Peer(); }
+        for (romis_ctx* k : c->kids) romis_destroy(k);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->nodes, &c->tri_geom, &c->tri_attr, &c->materials, &c->tex_pixels, &c->tex_desc, &c->lights,
@@ -200,11 +225,13 @@ extern "C" void romis_destroy(romis_ctx* c) {
 
 extern "C" int romis_stream(romis_ctx* c, void** s) {
     if (!c || !s) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_stream");
     *s = (void*)c->stream; return ROMIS_OK;
 }
 
 extern "C" int romis_synchronize(romis_ctx* c) {
     if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_EACH(c, romis_synchronize(k));
     RCHECK(c, cudaSetDevice(c->device));
     RCHECK(c, cudaStreamSynchronize(c->stream));
     return ROMIS_OK;
@@ -235,6 +262,7 @@ extern "C" float romis_specular_cutoff(float shininess) {
 extern "C" int romis_upload_scene(romis_ctx* c, const romis_mesh_desc* meshes, int n_meshes,
                                   const romis_texture* textures, int n_textures) {
     if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) return group_upload_scene(c, meshes, n_meshes, textures, n_textures);
     if (n_meshes < 0 || n_textures < 0 || (n_meshes > 0 && !meshes) || (n_textures > 0 && !textures))
         return fail(c, ROMIS_ERR_INVALID, "romis_upload_scene: bad arguments");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_upload_scene: frame in flight");
@@ -492,16 +520,25 @@ static int upload_lights_impl(romis_ctx* c, const romis_light* lights, int n, in
     return ROMIS_OK;
 }
 
-extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) { return upload_lights_impl(c, lights, n, 0, n); }
+extern "C" int romis_upload_lights(romis_ctx* c, const romis_light* lights, int n) {
+    if (c && !c->kids.empty()) return group_upload_lights(c, lights, n, 0, n);
+    return upload_lights_impl(c, lights, n, 0, n);
+}
 
 extern "C" int romis_upload_lights_range(romis_ctx* c, const romis_light* lights, int n, int first_dirty, int n_dirty) {
+    if (c && !c->kids.empty()) return group_upload_lights(c, lights, n, first_dirty, n_dirty);
     return upload_lights_impl(c, lights, n, first_dirty, n_dirty);
 }
 
-extern "C" int romis_set_light_archive_auto(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->arch_auto = on != 0; return ROMIS_OK; }
+extern "C" int romis_set_light_archive_auto(romis_ctx* c, int on) {
+    if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_set_light_archive_auto");
+    c->arch_auto = on != 0; return ROMIS_OK;
+}
 
 extern "C" int romis_light_archive_marks(romis_ctx* c, uint8_t* marks, int capacity, int* n_slots) {
     if (!c || !n_slots || capacity < 0 || (capacity > 0 && !marks)) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_light_archive_marks");
     *n_slots = 0;
     if (!c->marks_pending) return ROMIS_OK;
     RCHECK(c, cudaSetDevice(c->device));
@@ -514,12 +551,14 @@ extern "C" int romis_light_archive_marks(romis_ctx* c, uint8_t* marks, int capac
 
 extern "C" int romis_light_archive_release(romis_ctx* c, const uint8_t* keep, int n_slots) {
     if (!c || n_slots < 0 || (n_slots > 0 && !keep)) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_light_archive_release");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_light_archive_release: frame in flight");
     return archive_harvest(c, keep, (uint32_t)n_slots);
 }
 
 extern "C" int romis_light_archive_size(romis_ctx* c, int* n_slots, int* n_held) {
     if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) c = c->kids[0];
     if (n_slots) *n_slots = (int)c->arch_orig.size();
     if (n_held) *n_held = (int)(c->arch_orig.size() - c->arch_free.size());
     return ROMIS_OK;
@@ -530,15 +569,28 @@ extern "C" int romis_light_archive_size(romis_ctx* c, int* n_slots, int* n_held)
 // ------------------------------------------------------------------------------------------------
 extern "C" int romis_set_band(romis_ctx* c, int y0, int y1) {
     if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_set_band");
     if (y0 < 0 || y1 < y0) return fail(c, ROMIS_ERR_INVALID, "romis_set_band: need 0 <= y0 <= y1");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_set_band: frame in flight");
     if (y0 != c->band_y0 || y1 != c->band_y1) { c->band_y0 = y0; c->band_y1 = y1; c->W = c->H = c->N = 0; c->history_valid = false; }
     return ROMIS_OK;
 }
 
-extern "C" int romis_reset_history(romis_ctx* c) { if (!c) return ROMIS_ERR_INVALID; c->history_valid = false; return ROMIS_OK; }
-extern "C" int romis_set_capture(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->capture = on != 0; return ROMIS_OK; }
-extern "C" int romis_set_stage_timing(romis_ctx* c, int on) { if (!c) return ROMIS_ERR_INVALID; c->stage_timing = on != 0; return ROMIS_OK; }
+extern "C" int romis_reset_history(romis_ctx* c) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_EACH(c, romis_reset_history(k));
+    c->history_valid = false; return ROMIS_OK;
+}
+extern "C" int romis_set_capture(romis_ctx* c, int on) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_EACH(c, romis_set_capture(k, on));
+    c->capture = on != 0; return ROMIS_OK;
+}
+extern "C" int romis_set_stage_timing(romis_ctx* c, int on) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_EACH(c, romis_set_stage_timing(k, on));
+    c->stage_timing = on != 0; return ROMIS_OK;
+}
 
 static int validate(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H, const romis_rng* rng) {
     if (!f || !cam || !rng) return fail(c, ROMIS_ERR_INVALID, "null features / camera / rng");
@@ -616,6 +668,7 @@ static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, in
 extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
                                  int history_valid, const romis_rng* rng) {
     if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_frame_begin");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_begin: previous frame not ended");
     int rc = validate(c, f, cam, W, H, rng);
     if (rc) return rc;
@@ -748,6 +801,7 @@ static HaloDev halo_for_pass(romis_ctx* c, int out, int pass, const dim3& grid, 
 // hit pixels (miss pixels short-circuit), so hosts use this profile as a first cut of the frame into equal-cost row bands.
 // Every rank computes the same profile from the same scene and camera, so the band edges agree without communication.
 extern "C" int romis_row_hit_counts(romis_ctx* c, const romis_camera* cam, int W, int H, uint32_t* hits_per_row) {
+    if (c && !c->kids.empty()) c = c->kids[0];
     if (!c || !cam || !hits_per_row || W < 1 || H < 1) return ROMIS_ERR_INVALID;
     if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_row_hit_counts: frame in flight");
@@ -776,6 +830,7 @@ extern "C" int romis_row_hit_counts(romis_ctx* c, const romis_camera* cam, int W
 }
 
 extern "C" int romis_band_prepare(romis_ctx* c, const romis_features* f, int W, int H) {
+    ROMIS_NOT_ON_GROUP(c, "romis_band_prepare");
     if (!c || !f) return ROMIS_ERR_INVALID;
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_band_prepare: frame in flight");
     if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "no scene uploaded");
@@ -791,6 +846,7 @@ extern "C" int romis_band_prepare(romis_ctx* c, const romis_features* f, int W, 
 }
 
 extern "C" int romis_peer_export(romis_ctx* c, void* blob) {
+    ROMIS_NOT_ON_GROUP(c, "romis_peer_export");
     if (!c || !blob) return ROMIS_ERR_INVALID;
     if (!c->W || !c->flags.p) return fail(c, ROMIS_ERR_STATE, "romis_peer_export: call romis_band_prepare first");
     RCHECK(c, cudaSetDevice(c->device));
@@ -811,6 +867,7 @@ static int attach_one(romis_ctx* c, int side, const void* blob) {
     if (b.W != c->W || b.H != c->H || b.N != c->N || b.row_stride != c->row_stride) return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: neighbour renders a different frame geometry");
     if ((side == 0 && b.y1 != c->y0) || (side == 1 && b.y0 != c->y1)) return fail(c, ROMIS_ERR_INVALID, "romis_peer_attach: bands are not adjacent");
     romis_ctx::Peer& p = c->peer[side];
+    p.ipc = true;
     for (int i = 0; i < 3; i++) RCHECK(c, cudaIpcOpenMemHandle((void**)&p.res[i], b.res[i], cudaIpcMemLazyEnablePeerAccess));
     RCHECK(c, cudaIpcOpenMemHandle((void**)&p.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
     p.y0 = b.y0; p.y1 = b.y1; p.ey0 = b.ey0; p.ey1 = b.ey1; p.row_stride = (size_t)b.row_stride;
@@ -819,14 +876,17 @@ static int attach_one(romis_ctx* c, int side, const void* blob) {
 }
 
 extern "C" int romis_peer_detach(romis_ctx* c) {
+    ROMIS_NOT_ON_GROUP(c, "romis_peer_detach");
     if (!c) return ROMIS_ERR_INVALID;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 2; s++) {
         romis_ctx::Peer& p = c->peer[s];
-        if (!p.on) continue;
-        for (int i = 0; i < 3; i++) if (p.res[i]) cudaIpcCloseMemHandle(p.res[i]);
-        if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        if (!p.on && !p.ipc) continue;
+        if (p.ipc) {
+            for (int i = 0; i < 3; i++) if (p.res[i]) cudaIpcCloseMemHandle(p.res[i]);
+            if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        }
         p = romis_ctx::Peer();
     }
     c->exported = false;
@@ -834,6 +894,7 @@ extern "C" int romis_peer_detach(romis_ctx* c) {
 }
 
 extern "C" int romis_peer_attach(romis_ctx* c, const void* low_blob, const void* high_blob) {
+    ROMIS_NOT_ON_GROUP(c, "romis_peer_attach");
     if (!c) return ROMIS_ERR_INVALID;
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_peer_attach: frame in flight");
     if (!c->W || !c->flags.p) return fail(c, ROMIS_ERR_STATE, "romis_peer_attach: call romis_band_prepare first");
@@ -849,6 +910,7 @@ extern "C" int romis_peer_attach(romis_ctx* c, const void* low_blob, const void*
 }
 
 extern "C" int romis_peer_error(romis_ctx* c, int* timed_out) {
+    ROMIS_NOT_ON_GROUP(c, "romis_peer_error");
     if (!c || !timed_out) return ROMIS_ERR_INVALID;
     *timed_out = 0;
     if (!c->flags.p) return ROMIS_OK;
@@ -861,6 +923,7 @@ extern "C" int romis_peer_error(romis_ctx* c, int* timed_out) {
 
 extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_frame_spatial_pass");
     if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_spatial_pass: no frame in flight");
     if (!c->fr.f.spatialReuse || pass != c->next_pass || pass >= (int)c->fr.f.spatialResamplingPasses)
         return fail(c, ROMIS_ERR_STATE, "romis_frame_spatial_pass: unexpected pass index");
@@ -885,8 +948,22 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     return ROMIS_OK;
 }
 
+static int frame_end_enqueue(romis_ctx* c, float* out_rgb);
+static int frame_end_wait(romis_ctx* c, float* out_rgb) {
+    if (out_rgb) {
+        RCHECK(c, cudaSetDevice(c->device));
+        RCHECK(c, cudaStreamSynchronize(c->copy_stream));
+        RCHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    return ROMIS_OK;
+}
 extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
     if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) return fail(c, ROMIS_ERR_INVALID, "stepwise frames are per-device calls: not available on a multi-device context");
+    int rc = frame_end_enqueue(c, out_rgb);
+    return rc ? rc : frame_end_wait(c, out_rgb);
+}
+static int frame_end_enqueue(romis_ctx* c, float* out_rgb) {
     if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_frame_end: no frame in flight");
     if (c->fr.f.spatialReuse && c->next_pass != (int)c->fr.f.spatialResamplingPasses)
         return fail(c, ROMIS_ERR_STATE, "romis_frame_end: spatial passes missing");
@@ -918,10 +995,6 @@ extern "C" int romis_frame_end(romis_ctx* c, float* out_rgb) {
     c->hist = c->cur;
     c->history_valid = true;
     c->in_frame = false;
-    if (out_rgb) {
-        RCHECK(c, cudaStreamSynchronize(c->copy_stream));
-        RCHECK(c, cudaStreamSynchronize(c->stream));
-    }
     return ROMIS_OK;
 }
 
@@ -937,9 +1010,170 @@ static int render_common(romis_ctx* c, const romis_features* f, const romis_came
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// multi-device context: ONE caller, ONE process, several GPUs (romis_create with n_devices > 1)
+// ------------------------------------------------------------------------------------------------
+// The reference calls its frame from one thread of one process (main.cpp:164, ui.cpp:161), so the drop-in must be able to use
+// every GPU of the box from there.  The parent context owns one child context per device; each child renders a row band of
+// the frame with the same kernels and the same fused halo exchange as the one-process-per-GPU mode, only the neighbours'
+// buffers are reached through cudaDeviceEnablePeerAccess instead of CUDA IPC.  All launches are asynchronous, so a single host
+// thread keeps every device busy; the bands' rows land in the caller's single out_rgb.  Band edges: equal COST from the
+// per-row hit profile (romis_row_hit_counts), fixed until the resolution, N or radius changes (moving an edge would drop the
+// rows' temporal history).
+static int group_fail(romis_ctx* g, romis_ctx* kid, int rc) { g->err = kid->err; return rc; }
+
+static int group_create(const int* device_ids, int n, romis_ctx** out, std::string& err) {
+    romis_ctx* g = new (std::nothrow) romis_ctx();
+    if (!g) { err = "out of host memory"; return ROMIS_ERR_NOMEM; }
+    g->device = device_ids[0];
+    for (int i = 0; i < n; i++) {
+        romis_ctx* k = nullptr;
+        int rc = romis_create(&device_ids[i], 1, &k);
+        if (rc != ROMIS_OK) { err = romis_last_error(nullptr); for (romis_ctx* q : g->kids) romis_destroy(q); delete g; return rc; }
+        k->arch_auto = false;           // the bands recycle light-archive slots together (group_upload_lights)
+        g->kids.push_back(k);
+    }
+    for (int i = 0; i < n; i++)         // neighbouring bands store into each other's halo rows
+        for (int j : {i - 1, i + 1}) {
+            if (j < 0 || j >= n || device_ids[j] == device_ids[i]) continue;
+            int can = 0;
+            cudaSetDevice(device_ids[i]);
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[j]);
+            if (e == cudaSuccess && can) { e = cudaDeviceEnablePeerAccess(device_ids[j], 0); if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; } }
+            if (e != cudaSuccess || !can) {
+                err = "device " + std::to_string(device_ids[i]) + " cannot map the memory of device " + std::to_string(device_ids[j]) + " (peer access)";
+                for (romis_ctx* q : g->kids) romis_destroy(q);
+                delete g; return ROMIS_ERR_CUDA;
+            }
+        }
+    *out = g;
+    return ROMIS_OK;
+}
+
+static void group_unwire(romis_ctx* g) {
+    for (romis_ctx* k : g->kids) { cudaSetDevice(k->device); if (k->stream) cudaStreamSynchronize(k->stream); k->peer[0] = romis_ctx::Peer(); k->peer[1] = romis_ctx::Peer(); k->exported = false; }
+    g->g_wired = false;
+}
+
+static std::vector<int> equal_cost_edges(const std::vector<double>& cost, int bands, int min_rows) {
+    const int H = (int)cost.size();
+    std::vector<double> prefix(H + 1, 0.0);
+    for (int y = 0; y < H; y++) prefix[y + 1] = prefix[y] + cost[y];
+    std::vector<int> e(1, 0);
+    for (int b = 1; b < bands; b++) {
+        const double target = prefix[H] * b / bands;
+        int cut = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        cut = std::max(cut, e.back() + min_rows);
+        cut = std::min(cut, H - (bands - b) * min_rows);
+        e.push_back(cut);
+    }
+    e.push_back(H);
+    return e;
+}
+
+// bands, buffers and neighbour wiring for (W, H, N, radius)
+static int group_prepare(romis_ctx* g, const romis_features* f, const romis_camera* cam, int W, int H) {
+    const int N = (int)f->numSamplesInReservoir, halo = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
+    if (g->g_wired && W == g->g_W && H == g->g_H && N == g->g_N && halo <= g->g_halo) return ROMIS_OK;
+    group_unwire(g);
+    const int min_rows = std::max(halo, 1);
+    const int active = std::max(1, std::min((int)g->kids.size(), H / min_rows));
+    std::vector<uint32_t> hits((size_t)H);
+    int rc = romis_row_hit_counts(g->kids[0], cam, W, H, hits.data());
+    if (rc) return group_fail(g, g->kids[0], rc);
+    std::vector<double> cost((size_t)H);
+    for (int y = 0; y < H; y++) cost[y] = hits[y] + 0.04 * (W - (double)hits[y]);      // miss pixels short-circuit every pass (measured ratio)
+    g->g_edges = equal_cost_edges(cost, active, min_rows);
+    for (int i = 0; i < active; i++) {
+        romis_ctx* k = g->kids[i];
+        if ((rc = romis_set_band(k, g->g_edges[i], g->g_edges[i + 1]))) return group_fail(g, k, rc);
+        if ((rc = romis_band_prepare(k, f, W, H))) return group_fail(g, k, rc);
+    }
+    for (int i = 0; i < active; i++)
+        for (int side = 0; side < 2; side++) {
+            const int j = side == 0 ? i - 1 : i + 1;
+            if (j < 0 || j >= active) continue;
+            romis_ctx* k = g->kids[i]; romis_ctx* nb = g->kids[j];
+            romis_ctx::Peer& p = k->peer[side];
+            for (int b = 0; b < 3; b++) p.res[b] = (unsigned char*)nb->res[b].p;
+            p.flags = (uint32_t*)nb->flags.p;
+            p.y0 = nb->y0; p.y1 = nb->y1; p.ey0 = nb->ey0; p.ey1 = nb->ey1; p.row_stride = nb->row_stride;
+            p.ipc = false; p.on = true;
+        }
+    g->g_active = active; g->g_W = W; g->g_H = H; g->g_N = N; g->g_halo = halo; g->g_wired = true;
+    return ROMIS_OK;
+}
+
+static int group_upload_scene(romis_ctx* g, const romis_mesh_desc* meshes, int n_meshes, const romis_texture* textures, int n_textures) {
+    group_unwire(g);
+    for (romis_ctx* k : g->kids) { int rc = romis_upload_scene(k, meshes, n_meshes, textures, n_textures); if (rc) return group_fail(g, k, rc); }
+    return ROMIS_OK;
+}
+
+static int group_upload_lights(romis_ctx* g, const romis_light* lights, int n, int first, int count) {
+    // halo rows carry light-archive slots from band to band: every band recycles the slots NO band's history holds
+    std::vector<uint8_t> keep;
+    for (romis_ctx* k : g->kids) {
+        if (!k->marks_pending) continue;
+        cudaSetDevice(k->device);
+        if (cudaEventSynchronize(k->ev_marks) != cudaSuccess) { g->err = "light archive marks"; return ROMIS_ERR_CUDA; }
+        if (keep.size() < k->marks_slots) keep.resize(k->marks_slots, 0);
+        for (uint32_t s = 0; s < k->marks_slots; s++) keep[s] |= k->arch_mark_host[s];
+    }
+    for (romis_ctx* k : g->kids) {
+        if (!keep.empty()) { int rc = archive_harvest(k, keep.data(), (uint32_t)keep.size()); if (rc) return group_fail(g, k, rc); }
+        int rc = upload_lights_impl(k, lights, n, first, count);
+        if (rc) return group_fail(g, k, rc);
+    }
+    return ROMIS_OK;
+}
+
+static int group_render_frame(romis_ctx* g, const romis_features* f, const romis_camera* cam, int W, int H, int history_valid,
+                              const romis_rng* rng, float* out_rgb) {
+    int rc = validate(g->kids[0], f, cam, W, H, rng);
+    if (rc) return group_fail(g, g->kids[0], rc);
+    if ((rc = group_prepare(g, f, cam, W, H))) return rc;
+    const int n = g->g_active;
+    auto abort_frame = [&](romis_ctx* k, int code) { for (int i = 0; i < n; i++) g->kids[i]->in_frame = false; return group_fail(g, k, code); };
+    for (int i = 0; i < n; i++) if ((rc = romis_frame_begin(g->kids[i], f, cam, W, H, history_valid, rng))) return abort_frame(g->kids[i], rc);
+    if (f->spatialReuse)
+        for (int p = 0; p < (int)f->spatialResamplingPasses; p++)
+            for (int i = 0; i < n; i++) if ((rc = romis_frame_spatial_pass(g->kids[i], p))) return abort_frame(g->kids[i], rc);
+    for (int i = 0; i < n; i++) if ((rc = frame_end_enqueue(g->kids[i], out_rgb))) return abort_frame(g->kids[i], rc);
+    for (int i = 0; i < n; i++) {
+        romis_ctx* k = g->kids[i];
+        if (out_rgb) rc = frame_end_wait(k, out_rgb);
+        else { cudaSetDevice(k->device); rc = cudaStreamSynchronize(k->stream) == cudaSuccess ? ROMIS_OK : ROMIS_ERR_CUDA; if (rc) k->err = "cudaStreamSynchronize"; }
+        if (rc) return group_fail(g, k, rc);
+        uint32_t timed_out = 0;
+        if (k->flags.p && (k->peer[0].on || k->peer[1].on)) {
+            cudaMemcpy(&timed_out, (uint32_t*)k->flags.p + 4, 4, cudaMemcpyDeviceToHost);
+            if (timed_out) { g->err = "a band waited for its neighbour's rows for more than 2 s (device " + std::to_string(k->device) + ")"; return ROMIS_ERR_CUDA; }
+        }
+    }
+    return ROMIS_OK;
+}
+
+static int group_timings(romis_ctx* g, romis_timings* out) {
+    romis_timings t; std::memset(&t, 0, sizeof t);
+    for (int i = 0; i < std::max(1, g->g_active); i++) {
+        romis_timings k; int rc = romis_last_frame_timings(g->kids[i], &k);
+        if (rc) return group_fail(g, g->kids[i], rc);
+        t.primary_ms = std::max(t.primary_ms, k.primary_ms); t.initial_ms = std::max(t.initial_ms, k.initial_ms);
+        t.temporal_ms = std::max(t.temporal_ms, k.temporal_ms); t.shade_ms = std::max(t.shade_ms, k.shade_ms);
+        t.total_ms = std::max(t.total_ms, k.total_ms); t.n_spatial = std::max(t.n_spatial, k.n_spatial);
+        for (int p = 0; p < 8; p++) { t.spatial_ms[p] = std::max(t.spatial_ms[p], k.spatial_ms[p]); t.exchange_ms[p] = std::max(t.exchange_ms[p], k.exchange_ms[p]); }
+        t.n_launches += k.n_launches;
+    }
+    *out = t;
+    return ROMIS_OK;
+}
+
 extern "C" int romis_render_frame(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
                                   int history_valid, const romis_rng* rng, float* out_rgb) {
     if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) return group_render_frame(c, f, cam, W, H, history_valid, rng, out_rgb);
     int rc = render_common(c, f, cam, W, H, history_valid, rng, out_rgb);
     if (rc == ROMIS_OK && !out_rgb) RCHECK(c, cudaStreamSynchronize(c->stream));
     return rc;
@@ -948,6 +1182,7 @@ extern "C" int romis_render_frame(romis_ctx* c, const romis_features* f, const r
 extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
                                          int history_valid, const romis_rng* rng, const float** dev_rgb) {
     if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "romis_render_frame_device (the image is spread over the devices)");
     int rc = render_common(c, f, cam, W, H, history_valid, rng, nullptr);
     if (rc == ROMIS_OK && dev_rgb) *dev_rgb = (const float*)c->rgb.p;
     return rc;
@@ -960,6 +1195,7 @@ extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, 
 static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
                             int W, int H, const romis_rng* rng, float* out_rgb) {
     if (!c) return ROMIS_ERR_INVALID;
+    ROMIS_NOT_ON_GROUP(c, "R-MIS / R-OMIS frames are not sharded");
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "frame in flight");
     if (!rp) return fail(c, ROMIS_ERR_INVALID, "null rmis parameters");
     int rc = validate(c, f, cam, W, H, rng);
@@ -1081,6 +1317,7 @@ extern "C" int romis_render_frame_romis(romis_ctx* c, const romis_features* f, c
 
 // Parity read-back of the last R-OMIS frame: matrices[H][W][K1][K1], contributions[H][W][3][K1]
 extern "C" int romis_download_romis_system(romis_ctx* c, float* matrices, float* contributions) {
+    ROMIS_NOT_ON_GROUP(c, "romis_download_romis_system");
     if (!c) return ROMIS_ERR_INVALID;
     if (!c->rmis_K1 || !c->romis_tech.p) return fail(c, ROMIS_ERR_STATE, "romis_download_romis_system: no R-OMIS frame rendered");
     RCHECK(c, cudaSetDevice(c->device));
@@ -1098,6 +1335,7 @@ extern "C" int romis_download_romis_system(romis_ctx* c, float* matrices, float*
 }
 
 extern "C" int romis_download_rmis_neighbours(romis_ctx* c, int32_t* xy, uint32_t* count) {
+    ROMIS_NOT_ON_GROUP(c, "romis_download_rmis_neighbours");
     if (!c) return ROMIS_ERR_INVALID;
     if (!c->rmis_K1 || !c->rmis_nb.p) return fail(c, ROMIS_ERR_STATE, "romis_download_rmis_neighbours: no R-MIS frame rendered");
     RCHECK(c, cudaSetDevice(c->device));
@@ -1118,6 +1356,7 @@ extern "C" int romis_download_rmis_neighbours(romis_ctx* c, int32_t* xy, uint32_
 }
 
 extern "C" int romis_halo_region(romis_ctx* c, int which, void** dev_ptr, size_t* bytes) {
+    ROMIS_NOT_ON_GROUP(c, "romis_halo_region");
     if (!c || !dev_ptr || !bytes) return ROMIS_ERR_INVALID;
     if (!c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_halo_region: no frame in flight");
     const int r = c->fr.f.spatialReuse ? (int)c->fr.f.spatialResampleRadius : 0;
@@ -1140,6 +1379,7 @@ extern "C" int romis_halo_region(romis_ctx* c, int which, void** dev_ptr, size_t
 // ------------------------------------------------------------------------------------------------
 extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
     if (!c || !out) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) return group_timings(c, out);
     RCHECK(c, cudaSetDevice(c->device));
     if (c->timings_pending) {
         RCHECK(c, cudaEventSynchronize(c->ev_end));
@@ -1172,6 +1412,7 @@ extern "C" int romis_last_frame_timings(romis_ctx* c, romis_timings* out) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int romis_download_reservoirs(romis_ctx* c, int pass_id, romis_reservoir_dump* out) {
     if (!c || !out) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_ACTIVE(c, romis_download_reservoirs(k, pass_id, out));      // every band writes its own rows
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "romis_download_reservoirs: frame in flight");
     if (!c->W) return fail(c, ROMIS_ERR_STATE, "romis_download_reservoirs: no frame rendered");
     RCHECK(c, cudaSetDevice(c->device));
@@ -1205,6 +1446,7 @@ extern "C" int romis_download_reservoirs(romis_ctx* c, int pass_id, romis_reserv
 
 extern "C" int romis_download_gbuffer(romis_ctx* c, romis_gbuffer_dump* out) {
     if (!c || !out) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) ROMIS_GROUP_ACTIVE(c, romis_download_gbuffer(k, out));
     if (!c->W) return fail(c, ROMIS_ERR_STATE, "romis_download_gbuffer: no frame rendered");
     RCHECK(c, cudaSetDevice(c->device));
     RCHECK(c, cudaStreamSynchronize(c->stream));
@@ -1225,6 +1467,7 @@ extern "C" int romis_download_gbuffer(romis_ctx* c, romis_gbuffer_dump* out) {
 
 extern "C" int romis_trace_rays(romis_ctx* c, const float* origins, const float* dirs, const float* tfar, int n, int any_hit,
                                 uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {
+    if (c && !c->kids.empty()) c = c->kids[0];
     if (!c) return ROMIS_ERR_INVALID;
     if (!c->has_scene) return fail(c, ROMIS_ERR_STATE, "romis_trace_rays: no scene");
     if (n < 0 || (n > 0 && (!origins || !dirs || !tfar || !hit))) return fail(c, ROMIS_ERR_INVALID, "romis_trace_rays: bad arguments");

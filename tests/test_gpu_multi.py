@@ -36,3 +36,80 @@ def test_two_gpu_bands_equal_rows_and_nccl_transport():
 
 def test_four_gpu_bands_c3_many_lights():
     _run(4, ["--width", "768", "--height", "432", "--frames", "3", "--config", "c3"], 29544)
+
+
+# ---- one process, several devices: romis_create(device_ids, n_devices > 1) ----
+def _devices(n):
+    """n distinct GPUs when the box has them, else the same GPU n times (two bands on one device: same code path, the
+    neighbours' buffers are then reached without peer mapping)."""
+    import torch
+    have = torch.cuda.device_count()
+    return list(range(n)) if have >= n else [0] * n
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_multi_device_context_equals_single_device_frame(n, oracle_factory):
+    """The reference's caller is one thread of one process (main.cpp:164): one context over n devices renders the frame as n row
+    bands into the caller's single image, bit-identical to the one-device frame and to the oracle, light edits included."""
+    import numpy as np
+    from romis_b200 import abi
+    from romis_b200.api import RestirRenderer
+    from romis_b200.scene import Features
+    from cases import NIGHTCLUB_CAM
+    from common import assert_bits_equal, load_scene
+    scene = load_scene("CornellNightClub")
+    feat = Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True)
+    W, H = 160, 120
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    multi = RestirRenderer(_devices(n)); multi.upload_scene(scene)
+    orc = oracle_factory(); orc.upload_scene(scene); orc.reset_history()
+    lights = scene.lights.copy()
+    try:
+        for fr in range(5):
+            if fr >= 2:
+                lights["c0"][fr::3] *= np.float32(0.9); lights["p0"][fr::7, 2] += np.float32(0.03)
+                multi.upload_lights(lights); orc.upload_lights(lights)
+            oimg = orc.render_frame(feat, cam, W, H, fr > 0, 31, fr)
+            gimg = multi.render_frame(feat, cam, W, H, fr > 0, 31, fr)
+            assert_bits_equal(gimg, oimg, f"{n}-device context, frame {fr} image vs oracle")
+            g, o = multi.reservoirs(abi.ROMIS_PASS_FINAL), orc.reservoirs(abi.ROMIS_PASS_FINAL)
+            for fld in ("light_id", "M", "u", "v", "W"):
+                assert_bits_equal(getattr(g, fld), getattr(o, fld), f"{n}-device context, frame {fr} final {fld}")
+        t = multi.timings()
+        assert t.total_ms > 0 and t.n_launches > 0
+    finally:
+        multi.close()
+
+
+def test_multi_device_context_rejects_per_device_calls():
+    from romis_b200.api import RestirRenderer, RomisError
+    from romis_b200.scene import Features, RmisParams
+    from cases import NIGHTCLUB_CAM
+    from common import load_scene
+    multi = RestirRenderer(_devices(2)); multi.upload_scene(load_scene("Cube"))
+    try:
+        for call in (lambda: multi.set_band(0, 8), lambda: multi.frame_begin(Features(), NIGHTCLUB_CAM, 16, 16, False, 1, 0),
+                     lambda: multi.render_frame_rmis(Features(), RmisParams(), NIGHTCLUB_CAM, 16, 16, 1, 0), lambda: multi.stream()):
+            with pytest.raises(RomisError, match="multi-device"):
+                call()
+        multi.render_frame(Features(), NIGHTCLUB_CAM, 32, 32, False, 1, 0)     # tiny frame, radius 10: fewer bands than devices
+    finally:
+        multi.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libromis_dropin.so")), reason="oracle/_ref/libromis_dropin.so not built")
+def test_dropin_on_two_devices_fills_the_reference_screen():
+    """integration/render_restir_gpu.cpp with ROMIS_DEVICES=a,b (own process: the drop-in creates its context once per thread):
+    Screen::pixels() equals the compiled reference's renderReSTIR bit for bit."""
+    devs = ",".join(str(d) for d in _devices(2))
+    code = ("import sys; sys.path[:0] = ['tests', 'tests/golden']\n"
+            "from oracle import pyoracle; from romis_b200.scene import Features; from cases import NIGHTCLUB_CAM; from common import assert_bits_equal, load_scene\n"
+            "lib = pyoracle.DropinLib(); lib.set_scene(load_scene('CornellNightClub')); lib.reset_history()\n"
+            "feat = Features(spatialResamplingPasses=3, initialSamplesVisibilityCheck=True)\n"
+            "for fr in range(3):\n"
+            "    cpu = lib.render_frame(feat, NIGHTCLUB_CAM, 96, 80, fr > 0, 314, fr, pyoracle.REF_FLAG_WHOLE_FRAME, dump=False).image\n"
+            "    gpu = lib.render_frame_gpu(feat, NIGHTCLUB_CAM, 96, 80, fr > 0, 314, fr)\n"
+            "    assert_bits_equal(gpu, cpu, f'frame {fr}')\n"
+            "print('dropin on devices " + devs + " ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, ROMIS_DEVICES=devs))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

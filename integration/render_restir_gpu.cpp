@@ -51,7 +51,7 @@ struct GpuState {
     bool lightsHooked = false, lightsAllDirty = true;
     int dirtyFirst = 0, dirtyEnd = 0;
     // Screen::pixels() storage registered as page-locked memory, so the read-back is an asynchronous DMA into it
-    void* pinnedPtr = nullptr; size_t pinnedBytes = 0;
+    void* pinnedPtr = nullptr; size_t pinnedBytes = 0; bool pinScreen = true;
     ~GpuState() {
         if (pinnedPtr) romis_host_unregister(pinnedPtr);
         if (misCtx) romis_destroy(misCtx);
@@ -165,6 +165,7 @@ void uploadLights(const Scene& scene) {
 float* screenStorage(Screen& screen) {
     std::vector<glm::vec3>& px = screen.pixels();
     void* p = px.data(); const size_t bytes = px.size() * sizeof(glm::vec3);
+    if (!g.pinScreen) return &px[0].x;
     if (p != g.pinnedPtr || bytes != g.pinnedBytes) {
         if (g.pinnedPtr) romis_host_unregister(g.pinnedPtr);
         g.pinnedPtr = nullptr; g.pinnedBytes = 0;
@@ -208,6 +209,9 @@ extern "C" void romis_dropin_release_screen(void) {
     if (g.pinnedPtr) romis_host_unregister(g.pinnedPtr);
     g.pinnedPtr = nullptr; g.pinnedBytes = 0;
 }
+
+// measurement knob: leave Screen::pixels() pageable (what the read-back costs without the registration)
+extern "C" void romis_dropin_set_pin_screen(int on) { if (!on) romis_dropin_release_screen(); g.pinScreen = on != 0; }
 
 // half extents of the image plane: Trackball keeps them private (trackball.h:55-56).  The maintainer either adds two
 // accessors or, as here, the caller provides them; they are tan(fovy/2) and aspect*tan(fovy/2) (trackball.cpp:26-27).

@@ -391,6 +391,44 @@ int ref_render_frame_dropin(const romis_features* f, const ref_camera_desc* cam,
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
     return 0;
 }
+// End-to-end timing of the drop-in as the application runs it: ONE Screen / Trackball living across the frames (main.cpp:56-65),
+// renderReSTIR_gpu called frame after frame with the grid it returned, wall clock around every call.  pin = 0 leaves
+// Screen::pixels() pageable.  edit_light != 0: one light's colour changes before every frame (ui.cpp:172-261).
+extern "C" void romis_dropin_set_pin_screen(int on);
+int ref_dropin_bench(const romis_features* f, const ref_camera_desc* cam, int W, int H, int frames, int pin, int edit_light, double* out_ms) {
+    if (!g_embree) { g_err = "no scene"; return -1; }
+    try {
+        const Features features = toFeatures(*f);
+        Window window("ref", glm::ivec2(W, H), OpenGLVersion::GL2, false);
+        Screen screen(glm::ivec2(W, H), false);
+        Trackball camera { &window, glm::radians(cam->fov_deg), cam->distance };
+        camera.setCamera(g3(cam->look_at), glm::radians(g3(cam->rotation_deg)), cam->distance);
+        const float halfH = std::tan(glm::radians(cam->fov_deg) / 2.0f);
+        romis_dropin_set_half_extents(window.getAspectRatio() * halfH, halfH);
+        romis_dropin_set_rng(0x5eed, 0);
+        romis_dropin_set_pin_screen(pin);
+        ScreenPinGuard unpin;
+        std::shared_ptr<ReservoirGrid> prev;
+        NullBuf nb; std::streambuf* old = std::cout.rdbuf(&nb);
+        for (int fr = 0; fr < frames; fr++) {
+            if (edit_light && !g_scene.lights.empty()) {
+                auto& l = g_scene.lights[0];
+                const float s = 1.0f + 1e-3f * float(1 + fr % 7);
+                if (auto* p = std::get_if<PointLight>(&l)) p->color *= s;
+                else if (auto* q = std::get_if<SegmentLight>(&l)) q->color0 *= s;
+                else std::get<ParallelogramLight>(l).color0 *= s;
+            }
+            auto t0 = std::chrono::steady_clock::now();
+            ReservoirGrid grid = renderReSTIR_gpu(prev, g_scene, camera, *g_embree, screen, features);
+            prev = std::make_shared<ReservoirGrid>(std::move(grid));                // main.cpp:165
+            out_ms[fr] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        std::cout.rdbuf(old);
+        romis_dropin_set_pin_screen(1);
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    return 0;
+}
+
 // mode 0: renderRMIS_gpu, 1: renderROMIS_gpu -- the reference's own objects through the GPU bodies of the other two estimators
 int ref_render_frame_mis_dropin(int mode, const romis_features* f, const romis_rmis_params* rp, const ref_camera_desc* cam, int W, int H,
                                 const romis_rng* rng, float* out_rgb) {

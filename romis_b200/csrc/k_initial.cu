@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_INITIAL) initial_kernel(SceneD
     res_finish(r, N, sc, c, es);
     if (fr.f.initialSamplesVisibilityCheck) {
         ROMIS_FOR_SUB(j, NT, N) {
+            if (r.W[j] == 0.0f) continue;                   // already 0 (pdf = 0 or nothing accepted): the ray cannot change it
             v3 pos, col; light_sample<true>(sc, r.light[j], r.u[j], r.v[j], pos, col);
             if (!visible(sc, c, pos)) r.W[j] = 0.0f;
         }

@@ -35,50 +35,97 @@ __device__ __forceinline__ bool are_similar(const romis_rmis_params& rp, uint32_
     return true;
 }
 
-// The window of one pixel, classified: bit i of `mask` (scan order, rows of the clipped window) = "similar".
-struct RmisWindow { int x0, x1, y0, y1, x, y; uint32_t mask[ROMIS_RMIS_WORDS]; };
+// The same predicate without early exits, for the window scan (441 evaluations per pixel at r = 10): the three criteria are
+// evaluated side by side and combined, which costs a few arithmetic instructions more than the early exits save in branches.
+__device__ __forceinline__ bool are_similar_flat(bool sameGeometry, float maxDepthFrac, float minNormalsDot, uint32_t n_meshes,
+                                                 float4 own, uint32_t own_gid, float4 nb, uint32_t nb_mesh) {
+    const uint32_t gr = nb_mesh == n_meshes ? 0u : nb_mesh;
+    const float depthFracDiff = fabsf(1.0f - (own.x / nb.x));
+    const float normalsDot = dot3(V3(own.y, own.z, own.w), V3(nb.y, nb.z, nb.w));
+    // the negations keep the reference's behaviour for NaNs: `a > b` and `a < b` are both false for a NaN
+    return (!sameGeometry || own_gid == gr) & !(depthFracDiff > maxDepthFrac) & !(normalsDot < minNormalsDot);
+}
 
-// std::sample (libstdc++ selection sampling, bits/stl_algo.h:5841-5905) of n out of the `size` window pixels of class
-// `cls`, in scan order, without materialising the list: one decision per element, two decisions per engine call while
-// unsampled^2 fits the 32-bit engine range (__gen_two_uniform_ints).  all = true copies the class without draws
-// (neighbour_selection.cpp:80).  Appends packed (y << 16 | x) entries at plane `no` of the pixel's neighbour column.
+// The window of one pixel, classified: bit i of `mask` (scan order over the rows of the clipped window, wx pixels per row) =
+// "similar"; the pixel's own bit stays clear and `own` remembers where it is (it belongs to neither class).
+struct RmisWindow { int x0, y0, wx, count, own; uint32_t mask[ROMIS_RMIS_WORDS]; };
+
+// word `wi` of the membership mask of class `cls` (true: similar, false: dissimilar = clear bits inside the window, own pixel excluded)
+__device__ __forceinline__ uint32_t class_word(const RmisWindow& w, bool cls, int wi) {
+    uint32_t v = w.mask[wi];
+    if (cls) return v;
+    v = ~v;
+    const int rest = w.count - wi * 32;                                 // window pixels from this word on
+    if (rest < 32) v &= (1u << rest) - 1u;
+    if ((w.own >> 5) == wi) v &= ~(1u << (w.own & 31));
+    return v;
+}
+
+// Walks the members of a class in scan order: select(m) returns the packed (y << 16 | x) position of the m-th member, for
+// non-decreasing m (the cursor only moves forward, so a whole class costs one pass over the mask words).
+struct ClassCursor {
+    int wi = 0; uint32_t base = 0;
+    __device__ __forceinline__ uint32_t select(const RmisWindow& w, bool cls, uint32_t m) {
+        uint32_t wv = class_word(w, cls, wi); uint32_t c = (uint32_t)__popc(wv);
+        while (m - base >= c) { base += c; wi++; wv = class_word(w, cls, wi); c = (uint32_t)__popc(wv); }
+        uint32_t t = wv;
+        for (uint32_t q = m - base; q != 0u; q--) t &= t - 1u;          // drop the q lowest members of the word
+        const int i = wi * 32 + (__ffs((int)t) - 1);
+        // i / wx for i < 3721, wx <= 61: (i + 0.5) / wx is at least 0.5 / 61 away from an integer, far beyond the approximation's error
+        const int row = (int)__fdividef((float)i + 0.5f, (float)w.wx);
+        return ((uint32_t)(w.y0 + row) << 16) | (uint32_t)(w.x0 + (i - row * w.wx));
+    }
+};
+
+// std::sample (libstdc++ selection sampling, bits/stl_algo.h:5841-5905) of n out of the `size` window pixels of class `cls`,
+// in scan order, without materialising the list: one decision per member, two decisions per engine call while unsampled^2
+// fits the 32-bit engine range (__gen_two_uniform_ints), in MEMBER space -- window positions are only looked up for the (at
+// most k) members that are taken.  all = true copies the class without draws (neighbour_selection.cpp:80).  Appends packed
+// (y << 16 | x) entries at plane `no` of the pixel's neighbour column.
 __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32_t size, uint32_t n, bool all,
                                            romis_stream_key ek, uint32_t& ec, uint32_t* __restrict__ col, size_t plane, int& no, int cap) {
     if (size == 0u) return;
     if (n > size) n = size;
     if (all) n = size;
     if (n == 0u) return;
-    uint32_t unsampled = size;
-    const bool two_mode = 0xffffffffu / unsampled >= unsampled;
-    bool in_pairs = two_mode, have_p1 = false; uint32_t p1 = 0u;
-    int i = 0;
-    for (int ny = w.y0; ny <= w.y1 && n != 0u; ny++) {
-        for (int nx = w.x0; nx <= w.x1; nx++, i++) {
-            if (ny == w.y && nx == w.x) continue;
-            if ((((w.mask[i >> 5] >> (i & 31)) & 1u) != 0u) != cls) continue;
-            bool take;
-            if (all) take = true;
-            else if (have_p1) { have_p1 = false; --unsampled; take = p1 < n; }
-            else {
-                if (in_pairs && unsampled < 2u) in_pairs = false;       // the pair loop's `unsampled >= 2` (:5870)
-                if (in_pairs) {
-                    const uint32_t b1 = unsampled - 1u;
-                    const uint32_t xx = lemire32(ek, ec, unsampled * b1);
-                    // xx / b1 and xx % b1: xx < unsampled * b1 <= 3721 * 3720 < 2^24 (r <= ROMIS_RMIS_MAX_R), so both operands are
-                    // exact floats, the quotient is below 3721 and the approximate division is off by less than one: one fix-up step
-                    uint32_t p0 = (uint32_t)__fdividef((float)xx, (float)b1);
-                    int32_t rem = (int32_t)(xx - p0 * b1);
-                    if (rem < 0) { p0--; rem += (int32_t)b1; } else if (rem >= (int32_t)b1) { p0++; rem -= (int32_t)b1; }
-                    p1 = (uint32_t)rem; have_p1 = true;
-                    --unsampled; take = p0 < n;
-                } else { --unsampled; take = lemire32(ek, ec, unsampled + 1u) < n; }
-            }
-            if (take) {
-                if (no < cap) col[(size_t)no * plane] = ((uint32_t)ny << 16) | (uint32_t)nx;    // the grid holds k + 1 planes (host rejects what needs more)
-                no++; --n; if (n == 0u) break;
-            }
+    // The decisions of different pixels fall at different members, so a lane that looked its pick up on the spot would do so
+    // alone (measured: a third of the kernel's issue slots at 1.2 active lanes).  Picks are only noted (member index) and the
+    // window positions are looked up after the sampling loop, by all lanes of the warp together.
+    uint32_t taken[ROMIS_MAX_K + 1]; int nt = 0;
+    const int room = cap - no;
+    auto emit = [&](uint32_t m) { if (nt < room) taken[nt] = m; nt++; --n; };    // the grid holds k + 1 planes (host rejects what needs more)
+    auto flush = [&]() {
+        ClassCursor cur;
+        const int cnt = nt < room ? nt : room;
+        for (int t = 0; t < cnt; t++) col[(size_t)(no + t) * plane] = cur.select(w, cls, taken[t]);
+        no += nt;
+    };
+    if (all) {
+        ClassCursor cur;
+        for (uint32_t m = 0; m < size; m++) { if (no < cap) col[(size_t)no * plane] = cur.select(w, cls, m); no++; }
+        return;
+    }
+    uint32_t unsampled = size, m = 0;
+    if (0xffffffffu / unsampled >= unsampled) {                         // two decisions per engine call (:5866-5885)
+        while (n != 0u && unsampled >= 2u) {
+            const uint32_t b1 = unsampled - 1u;
+            const uint32_t xx = lemire32(ek, ec, unsampled * b1);
+            // xx / b1 and xx % b1: xx < unsampled * b1 <= 3721 * 3720 < 2^24 (r <= ROMIS_RMIS_MAX_R), so both operands are
+            // exact floats, the quotient is below 3721 and the approximate division is off by less than one: one fix-up step
+            uint32_t p0 = (uint32_t)__fdividef((float)xx, (float)b1);
+            int32_t rem = (int32_t)(xx - p0 * b1);
+            if (rem < 0) { p0--; rem += (int32_t)b1; } else if (rem >= (int32_t)b1) { p0++; rem -= (int32_t)b1; }
+            unsampled -= 2u;
+            if (p0 < n) { emit(m); if (n == 0u) break; }
+            if ((uint32_t)rem < n) emit(m + 1u);
+            m += 2u;
         }
     }
+    while (n != 0u && unsampled != 0u) {                                // one decision per engine call (:5888-5895)
+        if (lemire32(ek, ec, unsampled) < n) emit(m);
+        --unsampled; m++;
+    }
+    flush();
 }
 
 // generateResampleIndicesGrid: indicesRandom (neighbour_selection.cpp:24-45) / indicesSimilarity (:47-105)
@@ -91,34 +138,40 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
     romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_RMIS_NEIGH, (uint32_t)p, ROMIS_STREAM_ENGINE);
     uint32_t ec = 0;
     int no = 0;
-    RmisWindow w;
-    w.x = x; w.y = y;
-    w.x0 = max(0, x - r); w.x1 = min(fr.W - 1, x + r);
-    w.y0 = max(0, y - r); w.y1 = min(fr.H - 1, y + r);
+    const int wx0 = max(0, x - r), wx1 = min(fr.W - 1, x + r), wy0 = max(0, y - r), wy1 = min(fr.H - 1, y + r);
     col[0] = ((uint32_t)y << 16) | (uint32_t)x; no = 1;                            // :40 / :71 the pixel itself, always
     if (rm.p.neighbourSelectionStrategy == ROMIS_NEIGHBOURS_RANDOM) {
         for (int i = 0; i < k; i++) {
             // `glm::ivec2(distrX(gen), distrY(gen))` (:42): the order of the two draws is unspecified in C++; g++, which
             // builds the compiled reference the oracle is pinned against, evaluates them right to left: y first
-            int ny = romis_rng_uniform_int(romis_rng_bits(ek, ec++), w.y0, w.y1);
-            int nx = romis_rng_uniform_int(romis_rng_bits(ek, ec++), w.x0, w.x1);
+            int ny = romis_rng_uniform_int(romis_rng_bits(ek, ec++), wy0, wy1);
+            int nx = romis_rng_uniform_int(romis_rng_bits(ek, ec++), wx0, wx1);
             col[(size_t)no * rm.plane] = ((uint32_t)ny << 16) | (uint32_t)nx; no++;
         }
     } else {
-        // classify the window (:59-72)
+        // classify the window (:59-72): one bit per window pixel, 32 pixels per mask word
+        RmisWindow w;
+        w.x0 = wx0; w.y0 = wy0; w.wx = wx1 - wx0 + 1; w.count = w.wx * (wy1 - wy0 + 1); w.own = (y - wy0) * w.wx + (x - wx0);
         const float4 own = g.tn[p]; const uint32_t own_mesh = g.mesh[p];
-        uint32_t ns = 0, nd = 0, word = 0; int i = 0;
-        for (int ny = w.y0; ny <= w.y1; ny++) {
-            const size_t row = (size_t)ny * fr.W;
-            for (int nx = w.x0; nx <= w.x1; nx++, i++) {
-                if (!(ny == y && nx == x)) {
-                    const bool s = are_similar(rm.p, (uint32_t)sc.n_meshes, own, own_mesh, g.tn[row + nx], g.mesh[row + nx]);
-                    if (s) { ns++; word |= 1u << (i & 31); } else nd++;
-                }
-                if ((i & 31) == 31) { w.mask[i >> 5] = word; word = 0; }
+        const uint32_t own_gid = own_mesh == (uint32_t)sc.n_meshes ? 0u : own_mesh;    // a miss pixel keeps the value-initialised geometryId 0
+        const bool sameGeometry = rm.p.neighbourSameGeometry != 0;
+        const float maxDepthFrac = rm.p.neighbourMaxDepthDifferenceFraction, minNormalsDot = rm.p.neighbourMaxNormalAngleDifferenceRadians;
+        uint32_t ns = 0, word = 0; int bit = 0, wi = 0;
+        for (int ny = wy0; ny <= wy1; ny++) {
+            const float4* __restrict__ trow = g.tn + (size_t)ny * fr.W + wx0;
+            const uint32_t* __restrict__ mrow = g.mesh + (size_t)ny * fr.W + wx0;
+            _Pragma("unroll 3") for (int cx = 0; cx < w.wx; cx++) {
+                const bool s = are_similar_flat(sameGeometry, maxDepthFrac, minNormalsDot, (uint32_t)sc.n_meshes, own, own_gid, trow[cx], mrow[cx]);
+                word |= (s ? 1u : 0u) << bit;
+                if (++bit == 32) { w.mask[wi++] = word; ns += (uint32_t)__popc(word); word = 0u; bit = 0; }
             }
         }
-        if (i & 31) w.mask[i >> 5] = word;
+        if (bit) { w.mask[wi] = word; ns += (uint32_t)__popc(word); }
+        {   // the pixel itself is in neither class (:64)
+            uint32_t& ow = w.mask[w.own >> 5];
+            if ((ow >> (w.own & 31)) & 1u) { ow &= ~(1u << (w.own & 31)); ns--; }
+        }
+        const uint32_t nd = (uint32_t)w.count - 1u - ns;
         const uint32_t ku = (uint32_t)k;
         if (rm.p.neighbourSelectionStrategy == ROMIS_NEIGHBOURS_SIMILAR) {          // :79-85
             if (ns < ku) {

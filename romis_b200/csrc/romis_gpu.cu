@@ -1436,7 +1436,12 @@ extern "C" int romis_download_reservoirs(romis_ctx* c, int pass_id, romis_reserv
         launch_dump(c->stream, grid_for(c->W, c->y1 - c->y0), kBlock, c->sc, c->fr, b, c->N, (const uint32_t*)c->arch_orig_dev.p, (uint32_t*)slots[0].dev, (float*)slots[1].dev,
                     (float*)slots[2].dev, (float*)slots[3].dev, (uint32_t*)slots[4].dev, (float*)slots[5].dev, (float*)slots[6].dev);
         cudaError_t e = cudaGetLastError();
-        for (auto& s : slots) if (s.host && e == cudaSuccess) e = cudaMemcpyAsync(s.host, s.dev, n * s.elem, cudaMemcpyDeviceToHost, c->stream);
+        // only this band's rows are written (every band of a multi-device context fills its own part of the caller's arrays)
+        const size_t first = (size_t)c->y0 * c->W, cnt = (size_t)(c->y1 - c->y0) * c->W, plane = (size_t)c->H * c->W;
+        for (auto& s : slots) if (s.host)
+            for (int j = 0; j < c->N && e == cudaSuccess; j++)
+                e = cudaMemcpyAsync((char*)s.host + ((size_t)j * plane + first) * s.elem, (char*)s.dev + ((size_t)j * plane + first) * s.elem,
+                                    cnt * s.elem, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(c, ROMIS_ERR_CUDA, std::string("romis_download_reservoirs: ") + cudaGetErrorString(e));
     }

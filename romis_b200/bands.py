@@ -43,6 +43,27 @@ def balanced_band_edges(row_cost, world_size: int, min_rows: int):
     return edges
 
 
+def refine_band_edges(edges, times, row_profile, min_rows: int, fixed_frac: float = 0.4):
+    """One refinement step of the band edges from measured per-band times (BandedRenderer.calibrate).
+
+    A band's time is not proportional to its rows: every pass kernel has a latency floor (launch, one wave of blocks whose
+    threads run ~1e4 dependent instructions), so t = a + sum of the rows' costs with `a` a sizeable part of a thin band's
+    time.  Taking t / rows as the cost density makes narrow bands look expensive and the iteration over-correct; the part
+    `fixed_frac * mean(t)` is therefore taken off first.  Inside a band the remaining cost is spread like `row_profile`
+    (hit pixels per row: the only shape information there is), not uniformly.  Returns the new edges."""
+    import numpy as np
+    world = len(edges) - 1
+    t = np.asarray(times, np.float64)
+    prof = np.maximum(np.asarray(row_profile, np.float64), 1e-9)
+    a = fixed_frac * float(t.mean())
+    cost = np.zeros(len(prof))
+    for g in range(world):
+        lo, hi = edges[g], edges[g + 1]
+        var = max(t[g] - a, 0.25 * t[g])
+        cost[lo:hi] = var * prof[lo:hi] / prof[lo:hi].sum()
+    return balanced_band_edges(cost, world, min_rows)
+
+
 def check_bands(height: int, world_size: int, radius: int) -> None:
     smallest = min(band_rows(height, world_size, r)[1] - band_rows(height, world_size, r)[0] for r in range(world_size))
     if world_size > 1 and smallest < radius:
@@ -180,20 +201,23 @@ class BandedRenderer:
         self.edges = balanced_band_edges(hits + miss_cost * (W - hits), self.world_size, max(radius, 1))
         self._height = None
 
-    def calibrate(self, features, camera, W: int, H: int, seed: int = 1, rounds: int = 3, frames: int = 3):
+    def calibrate(self, features, camera, W: int, H: int, seed: int = 1, rounds: int = 6, frames: int = 3, tolerance: float = 0.03):
         """Measured refinement of the band edges (static camera): render a few frames, take every rank's own compute time
-        (all pass kernels; the wait for the neighbours' halo rows is timed separately), turn it into a per-row cost density
-        and recut.  Cost per hit pixel varies across the
-        image (e.g. surfaces facing away from most lights take the `NL < 0` early exit), which the hit-count profile
-        cannot see.  Moving an edge re-allocates the band, so history is dropped and peers are re-attached: call this
-        before the frames that matter."""
+        (all pass kernels; the wait for the neighbours' halo rows is timed separately) and recut with `refine_band_edges`;
+        up to `rounds` times, until the slowest band is within `tolerance` of the mean, and the best cut seen is kept.  Cost
+        per hit pixel varies across the image (e.g. surfaces facing away from most lights take the `NL < 0` early exit),
+        which the hit-count profile cannot see.  Moving an edge re-allocates the band, so history is dropped and peers are
+        re-attached: call this before the frames that matter."""
         import numpy as np
         if self.world_size == 1:
             return
         radius = features.spatialResampleRadius if features.spatialReuse else 0
         if self.edges is None:
             self.edges = [band_rows(H, self.world_size, g)[0] for g in range(self.world_size)] + [H]
-        for _ in range(rounds):
+        hits = self.r.row_hit_counts(camera, W, H).astype("float64")
+        profile = hits + 0.04 * (W - hits)
+
+        def measure():
             self.r.set_stage_timing(True)
             t_local = 0.0
             for fr in range(frames + 1):
@@ -205,17 +229,32 @@ class BandedRenderer:
             self.r.set_stage_timing(False)
             times = [None] * self.world_size
             dist.all_gather_object(times, t_local / frames)
-            cost = np.zeros(H)
-            for g in range(self.world_size):
-                a, b = self.edges[g], self.edges[g + 1]
-                cost[a:b] = times[g] / max(1, b - a)
-            new_edges = balanced_band_edges(cost, self.world_size, max(radius, 1))
+            return times
+
+        def move_to(edges):
+            if edges != self.edges:
+                if self._attached is not None:
+                    self._detach_all()
+                self.edges = list(edges)
+                self._height = None
+
+        best = None                                         # (slowest band's time, edges)
+        for _ in range(rounds):
+            times = measure()
+            if best is None or max(times) < best[0]:
+                best = (max(times), list(self.edges))
+            if max(times) <= (1.0 + tolerance) * (sum(times) / len(times)):
+                break
+            new_edges = refine_band_edges(self.edges, times, profile, max(radius, 1))
             if new_edges == self.edges:
                 break
-            if self._attached is not None:
-                self._detach_all()
-            self.edges = new_edges
-            self._height = None
+            move_to(new_edges)
+        else:
+            times = measure()                               # the cut of the last round has not been timed yet
+            if max(times) < best[0]:
+                best = (max(times), list(self.edges))
+        move_to(best[1])
+        self.calibration = {"slowest_ms": best[0], "edges": list(best[1])}
         self.r.reset_history()
 
     def band(self, height: int):

@@ -14,7 +14,10 @@ __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, 
     v3 d = gen_ray_dir(fr.cam, x, y, fr.W, fr.H);
     float t, u, v; uint32_t tri;
     size_t p = (size_t)(y - fr.ey0) * fr.W + x;
-    if (trace_closest(sc, fr.cam.origin, d, FLT_MAX, t, u, v, tri)) {
+    const bool hit = trace_closest(sc, fr.cam.origin, d, FLT_MAX, t, u, v, tri);
+    pdl_wait();                                     // the kernel before this one (the previous frame's) may still read the G-buffer
+    pdl_launch_dependents();
+    if (hit) {
         const float4* a = sc.tri_attr + 4 * (size_t)tri;
         float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2), a3 = __ldg(a + 3);
         float w = (1.0f - u) - v;                       // attribute interpolation (w*a + u*b) + v*c, oracle/tracer.h
@@ -37,14 +40,16 @@ __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, 
 // final shading + tone mapping -> Screen layout (row-flipped float RGB)
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
+__global__ void __launch_bounds__(ROMIS_LBT_SHADE, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
-    PixCtx c = make_ctx(sc, fr, g, x, y);
+    PixCtx c = make_ctx(sc, fr, g, x, y);            // G-buffer only: older than the previous kernel
+    pdl_wait();
+    pdl_launch_dependents();
     v3 color = V3(0, 0, 0);
     // Miss pixels shade to exactly +0 (computeShading is 0, W is 0); a sample with W == 0 adds (+-0) and leaves the sum
     // unchanged whatever its visibility: both skip the shadow ray and the shading without changing a bit.
@@ -176,10 +181,10 @@ __global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, const ui
 
 
 void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1) {
-    primary_kernel<<<grid, block, 0, s>>>(sc, fr, g, row0, row1);
+    launch_pdl(primary_kernel, grid, block, s, sc, fr, g, row0, row1);
 }
 void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb) {
-    ROMIS_DISPATCH_N(N, (shade_kernel<NT><<<grid, block, 0, s>>>(sc, fr, g, in, rgb)));
+    ROMIS_DISPATCH_N(N, (launch_pdl(shade_kernel<NT>, grid, block, s, sc, fr, g, in, rgb)));
 }
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {

@@ -44,6 +44,9 @@ __device__ __forceinline__ void spatial_pixel(const SceneDev& sc, const FrameDev
         }
         if (keep) stream[ns++] = ((uint32_t)nrow << 16) | (uint32_t)nx;
     }
+    // Everything above read the G-buffer only, which is older than the previous kernel; `in` is the previous kernel's output.
+    pdl_wait();
+    pdl_launch_dependents();
     // Phase 2 -- stream the selected reservoirs through Reservoir::update in order (reservoir.cpp:42-53); the records of
     // entry s+1 are fetched while entry s is being evaluated.  Self goes last (:124) and outside the loop: every lane of
     // the warp reaches it together, and its target pdf at this pixel is stored with the record, so the warp skips the
@@ -165,18 +168,18 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(S
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                     const ResBuf& in, const ResBuf& out, int pass) {
     const bool es = fr.f.enableShading != 0;
-    if (unbiased && es) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, true, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
-    else if (unbiased) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, true, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
-    else if (es) { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, false, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
-    else { ROMIS_DISPATCH_N(N, (spatial_kernel<NT, false, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass))); }
+    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass))); }
+    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass))); }
+    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass))); }
 }
 
 void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                          const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd) {
     const bool es = fr.f.enableShading != 0;
-    if (unbiased && es) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, true, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
-    else if (unbiased) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, true, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
-    else if (es) { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, false, true><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
-    else { ROMIS_DISPATCH_N(N, (spatial_halo_kernel<NT, false, false><<<grid, block, 0, s>>>(sc, fr, g, in, out, pass, hd))); }
+    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
+    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
+    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
 }
 }  // namespace romis

@@ -8,10 +8,12 @@ namespace romis {
 // temporal reuse: same-pixel predecessor, M clamp, biased combine of {current, predecessor}
 // ------------------------------------------------------------------------------------------------
 template <int NT, bool ES>        // ES: enableShading known to be on, see spatial_kernel
-__global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
+__global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
+    pdl_wait();                                     // `cur` comes from the kernel before this one
+    pdl_launch_dependents();
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = ES || fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_TEMPORAL) temporal_kernel(Scen
 
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                      const ResBuf& cur, const ResBuf& prev, const ResBuf& out) {
-    if (fr.f.enableShading) { ROMIS_DISPATCH_N(N, (temporal_kernel<NT, true><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out))); }
-    else { ROMIS_DISPATCH_N(N, (temporal_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, cur, prev, out))); }
+    if (fr.f.enableShading) { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, true>, grid, block, s, sc, fr, g, cur, prev, out))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, false>, grid, block, s, sc, fr, g, cur, prev, out))); }
 }
 }  // namespace romis

@@ -2,7 +2,22 @@
 #pragma once
 #include "device_common.cuh"
 
+#include <cstdlib>
+#include <utility>
+
 namespace romis {
+// Launch with programmatic stream serialisation (see pdl_wait in device_common.cuh); ROMIS_PDL=0 in the environment turns it off.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    static const bool on = [] { const char* e = std::getenv("ROMIS_PDL"); return !e || std::atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1);
 void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
                     float* wsum = nullptr, float* chosen = nullptr);

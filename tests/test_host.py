@@ -88,3 +88,23 @@ def test_equal_cost_band_edges():
     assert (np.diff(e) >= 10).all() and e[-1] == 100
     with pytest.raises(ValueError):
         balanced_band_edges(np.ones(30), 4, 10)
+
+
+def test_refine_band_edges_converges_with_latency_floor():
+    """Band times follow t = a + sum(row cost) with a large fixed part `a` (the thin-band latency floor): the refinement
+    must still converge to near-equal times (the naive density t / rows over-corrects), and keep every band >= min_rows."""
+    from romis_b200.bands import refine_band_edges
+    rng = np.random.default_rng(3)
+    H, world, a = 1080, 8, 0.25
+    y = np.arange(H)
+    true_cost = (0.2 + np.exp(-((y - 600) / 250.0) ** 2)) * (1.0 + 0.1 * rng.random(H))
+    true_cost *= 2.2 / true_cost.sum()
+    profile = np.maximum(true_cost * (1.0 + 0.3 * np.sin(y / 40.0)), 1e-3)      # the hit profile only resembles the true cost
+    edges = [g * H // world for g in range(world)] + [H]
+    times_of = lambda e: [a + true_cost[e[g]:e[g + 1]].sum() for g in range(world)]
+    spread0 = max(times_of(edges)) / np.mean(times_of(edges))
+    for _ in range(6):
+        edges = refine_band_edges(edges, times_of(edges), profile, 10)
+    t = times_of(edges)
+    assert max(t) / np.mean(t) < 1.03 < spread0
+    assert min(np.diff(edges)) >= 10 and edges[0] == 0 and edges[-1] == H

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) primary_kernel(SceneDev sc, FrameDev fr, 
 // final shading + tone mapping -> Screen layout (row-flipped float RGB)
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(ROMIS_LBT_SHADE, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb) {
+__global__ void __launch_bounds__(ROMIS_LBT_SHADE, ROMIS_MINB_SHADE) shade_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, float* __restrict__ rgb, FineDev fd) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(ROMIS_LBT_SHADE, ROMIS_MINB_SHADE) shade_kerne
     const bool es = fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
     PixCtx c = make_ctx(sc, fr, g, x, y);            // G-buffer only: older than the previous kernel
-    pdl_wait();
+    { const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y); fine_wait(fd, by0, by0 + (int)blockDim.y); }
     pdl_launch_dependents();
     v3 color = V3(0, 0, 0);
     // Miss pixels shade to exactly +0 (computeShading is 0, W is 0); a sample with W == 0 adds (+-0) and leaves the sum
@@ -183,8 +183,9 @@ __global__ void dump_kernel(SceneDev sc, FrameDev fr, ResBuf in, int N, const ui
 void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1) {
     launch_pdl(primary_kernel, grid, block, s, sc, fr, g, row0, row1);
 }
-void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb) {
-    ROMIS_DISPATCH_N(N, (launch_pdl(shade_kernel<NT>, grid, block, s, sc, fr, g, in, rgb)));
+void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb,
+                  const FineDev& fd) {
+    ROMIS_DISPATCH_N(N, (launch_pdl(shade_kernel<NT>, grid, block, s, sc, fr, g, in, rgb, fd)));
 }
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri) {

@@ -11,7 +11,7 @@ namespace romis {
 // path reads, stop occupying registers in a kernel that is short of them (measured: -3.5 %).  !ES reads the flag at run time.
 template <int NT, bool UNBIASED, bool ES>
 __device__ __forceinline__ void spatial_pixel(const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const ResBuf& out, int pass,
-                                              int x, int y, const HaloDev* hd) {
+                                              int x, int y, const HaloDev* hd, const FineDev& fd, int by0, int by1) {
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = ES || fr.f.enableShading != 0;
     const int lrow = y - fr.ey0;
@@ -45,7 +45,7 @@ __device__ __forceinline__ void spatial_pixel(const SceneDev& sc, const FrameDev
         if (keep) stream[ns++] = ((uint32_t)nrow << 16) | (uint32_t)nx;
     }
     // Everything above read the G-buffer only, which is older than the previous kernel; `in` is the previous kernel's output.
-    pdl_wait();
+    fine_wait(fd, by0, by1);
     pdl_launch_dependents();
     // Phase 2 -- stream the selected reservoirs through Reservoir::update in order (reservoir.cpp:42-53); the records of
     // entry s+1 are fetched while entry s is being evaluated.  Self goes last (:124) and outside the loop: every lane of
@@ -110,11 +110,13 @@ __device__ __forceinline__ void spatial_pixel(const SceneDev& sc, const FrameDev
 }
 
 template <int NT, bool UNBIASED, bool ES>
-__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass, FineDev fd) {
     int x, y; thread_pixel<true>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
-    spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, nullptr);
+    const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y), by1 = by0 + (int)blockDim.y;
+    spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, nullptr, fd, by0, by1);
+    fine_signal(fd, by0, by1);
 }
 
 // The same pass for a band with peer-mapped neighbours (fused halo exchange).  Row groups next to a band edge are launched
@@ -130,7 +132,7 @@ __device__ __forceinline__ void halo_spin(const uint32_t* f, uint32_t token, uin
     }
 }
 template <int NT, bool UNBIASED, bool ES>
-__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass, HaloDev hd) {
+__global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass, HaloDev hd, FineDev fd) {
     int by = (int)blockIdx.y;
     if (by >= hd.nl) by = by < hd.nl + hd.nh ? hd.gh0 + (by - hd.nl) : hd.nl + (by - hd.nl - hd.nh);
     const int gy0 = fr.y0 + by * (int)blockDim.y, gy1 = gy0 + (int)blockDim.y;
@@ -146,7 +148,9 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(S
     }
     int x, y; thread_pixel<true>(x, y, by);
     y += fr.y0;
-    if (x < fr.W && y < fr.y1) spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, &hd);
+    if (x >= fr.W || y >= fr.y1) return;            // the barriers below are among the live threads
+    spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, &hd, fd, gy0, gy1);
+    fine_signal(fd, gy0, gy1);
     if (edge0 || edge1) {
         __threadfence_system();
         __syncthreads();
@@ -166,20 +170,20 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(S
 
 
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                    const ResBuf& in, const ResBuf& out, int pass) {
+                    const ResBuf& in, const ResBuf& out, int pass, const FineDev& fd) {
     const bool es = fr.f.enableShading != 0;
-    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass))); }
-    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass))); }
-    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass))); }
-    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass))); }
+    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass, fd))); }
+    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass, fd))); }
+    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass, fd))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass, fd))); }
 }
 
 void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd) {
+                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd, const FineDev& fd) {
     const bool es = fr.f.enableShading != 0;
-    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
-    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
-    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
-    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass, hd))); }
+    if (unbiased && es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, true>, grid, block, s, sc, fr, g, in, out, pass, hd, fd))); }
+    else if (unbiased) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, true, false>, grid, block, s, sc, fr, g, in, out, pass, hd, fd))); }
+    else if (es) { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, true>, grid, block, s, sc, fr, g, in, out, pass, hd, fd))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(spatial_halo_kernel<NT, false, false>, grid, block, s, sc, fr, g, in, out, pass, hd, fd))); }
 }
 }  // namespace romis

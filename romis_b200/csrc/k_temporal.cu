@@ -8,7 +8,7 @@ namespace romis {
 // temporal reuse: same-pixel predecessor, M clamp, biased combine of {current, predecessor}
 // ------------------------------------------------------------------------------------------------
 template <int NT, bool ES>        // ES: enableShading known to be on, see spatial_kernel
-__global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out) {
+__global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) temporal_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf cur, ResBuf prev, ResBuf out, FineDev fd) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
@@ -41,12 +41,14 @@ __global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) tempo
     res_take_counts(r, N);
     res_finish(r, N, sc, c, es);
     res_store(out, lrow, x, r, N);
+    const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y);
+    fine_signal(fd, by0, by0 + (int)blockDim.y);
 }
 
 
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out) {
-    if (fr.f.enableShading) { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, true>, grid, block, s, sc, fr, g, cur, prev, out))); }
-    else { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, false>, grid, block, s, sc, fr, g, cur, prev, out))); }
+                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out, const FineDev& fd) {
+    if (fr.f.enableShading) { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, true>, grid, block, s, sc, fr, g, cur, prev, out, fd))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(temporal_kernel<NT, false>, grid, block, s, sc, fr, g, cur, prev, out, fd))); }
 }
 }  // namespace romis

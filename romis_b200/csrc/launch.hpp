@@ -22,12 +22,13 @@ void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, c
 void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
                     float* wsum = nullptr, float* chosen = nullptr);
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out);
+                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out, const FineDev& fd);
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                    const ResBuf& in, const ResBuf& out, int pass);
+                    const ResBuf& in, const ResBuf& out, int pass, const FineDev& fd);
 void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd);
-void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb);
+                         const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd, const FineDev& fd);
+void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb,
+                  const FineDev& fd);
 void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g);
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm);
 void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);

@@ -294,6 +294,11 @@ int romis_download_gbuffer(romis_ctx* ctx, romis_gbuffer_dump* out);
 int romis_trace_rays(romis_ctx* ctx, const float* origins, const float* dirs, const float* tfar, int n,
                      int any_hit, uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
 
+/* Self-test of the kernels' three-divisions-by-one-denominator routine (csrc/device_common.cuh div3_shared) against the plain
+ * IEEE division, both on the device: num n*3 floats, den n floats; out_fast / out_ref n*3 floats each, to be compared bit for
+ * bit by the caller.  No reference counterpart: the reference divides with glm's operator/ (shading.cpp:33). */
+int romis_selftest_division(romis_ctx* ctx, const float* num, const float* den, int n, float* out_fast, float* out_ref);
+
 /* ---- measurement ---- */
 typedef struct romis_timings {          /* device time of the last frame, milliseconds (CUDA events) */
     float primary_ms;

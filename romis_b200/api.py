@@ -28,7 +28,7 @@ EXPORTS = [
     "romis_render_frame_rmis", "romis_download_rmis_neighbours", "romis_specular_cutoff",
     "romis_render_frame_romis", "romis_download_romis_system",
     "romis_upload_lights_range", "romis_set_light_archive_auto", "romis_light_archive_marks", "romis_light_archive_release",
-    "romis_light_archive_size", "romis_host_register", "romis_host_unregister",
+    "romis_light_archive_size", "romis_host_register", "romis_host_unregister", "romis_selftest_division",
 ]
 PEER_BLOB_BYTES = 512
 
@@ -78,6 +78,7 @@ def load_library() -> C.CDLL:
     L.romis_download_reservoirs.argtypes = [vp, ci, C.POINTER(abi.romis_reservoir_dump)]
     L.romis_download_gbuffer.argtypes = [vp, C.POINTER(abi.romis_gbuffer_dump)]
     L.romis_trace_rays.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]
+    L.romis_selftest_division.argtypes = [vp, vp, vp, ci, vp, vp]
     L.romis_last_frame_timings.argtypes = [vp, C.POINTER(abi.romis_timings)]
     L.romis_row_hit_counts.argtypes = [vp, C.POINTER(abi.romis_camera), ci, ci, vp]
     L.romis_band_prepare.argtypes = [vp, C.POINTER(abi.romis_features), ci, ci]
@@ -354,6 +355,13 @@ class RestirRenderer:
         t = abi.romis_timings()
         self._check(self.lib.romis_last_frame_timings(self.ctx, C.byref(t)))
         return t
+
+    def selftest_division(self, num, den):
+        """(fast, plain) results of a / d per component on the device: div3_shared vs `/` (csrc/device_common.cuh)."""
+        num = np.ascontiguousarray(num, np.float32).reshape(-1, 3); den = np.ascontiguousarray(den, np.float32).reshape(-1)
+        fast = np.zeros_like(num); ref = np.zeros_like(num)
+        self._check(self.lib.romis_selftest_division(self.ctx, num.ctypes.data, den.ctypes.data, len(den), fast.ctypes.data, ref.ctypes.data))
+        return fast, ref
 
     def trace_rays(self, origins, dirs, tfar, any_hit=False):
         n = len(tfar)

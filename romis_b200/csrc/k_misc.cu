@@ -80,6 +80,20 @@ __global__ void trace_kernel(SceneDev sc, const float* __restrict__ o, const flo
     if (h) { t[i] = tt; u[i] = uu; v[i] = vv; tri[i] = ti; }
 }
 
+// div3_shared against the plain division (romis_selftest_division): out_fast / out_ref get the bits of both routes
+__global__ void division_selftest_kernel(const float* __restrict__ num, const float* __restrict__ den, int n, float* out_fast, float* out_ref) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const v3 a = V3(num[3 * i], num[3 * i + 1], num[3 * i + 2]);
+    const float d = den[i];
+    const v3 f = div3_shared(a, d), r = div3(a, d);
+    out_fast[3 * i] = f.x; out_fast[3 * i + 1] = f.y; out_fast[3 * i + 2] = f.z;
+    out_ref[3 * i] = r.x; out_ref[3 * i + 1] = r.y; out_ref[3 * i + 2] = r.z;
+}
+void launch_division_selftest(cudaStream_t s, const float* num, const float* den, int n, float* out_fast, float* out_ref) {
+    division_selftest_kernel<<<(n + 255) / 256, 256, 0, s>>>(num, den, n, out_fast, out_ref);
+}
+
 // hit pixels per image row (romis_row_hit_counts): one warp per row
 __global__ void row_hits_kernel(GBufDev g, int W, int H, uint32_t n_meshes, uint32_t* rows) {
     int y = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;

@@ -37,6 +37,7 @@ void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& f
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb);
 void launch_trace(cudaStream_t s, int n, const SceneDev& sc, const float* o, const float* d, const float* tfar, int any_hit,
                   uint8_t* hit, float* t, float* u, float* v, uint32_t* tri);
+void launch_division_selftest(cudaStream_t s, const float* num, const float* den, int n, float* out_fast, float* out_ref);
 void launch_row_hits(cudaStream_t s, const GBufDev& g, int W, int H, int n_meshes, uint32_t* rows);
 void launch_halo_push(cudaStream_t s, const void* src_low, void* dst_low, size_t bytes_low, const void* src_high, void* dst_high, size_t bytes_high,
                       const uint32_t* war_a, const uint32_t* war_b, uint32_t war_token, uint32_t* sig_a, uint32_t* sig_b, uint32_t token,

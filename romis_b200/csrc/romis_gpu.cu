@@ -1550,6 +1550,27 @@ extern "C" int romis_trace_rays(romis_ctx* c, const float* origins, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+extern "C" int romis_selftest_division(romis_ctx* c, const float* num, const float* den, int n, float* out_fast, float* out_ref) {
+    if (c && !c->kids.empty()) c = c->kids[0];
+    if (!c || !num || !den || !out_fast || !out_ref || n < 1) return ROMIS_ERR_INVALID;
+    RCHECK(c, cudaSetDevice(c->device));
+    DevBuf dn, dd, df, dr;
+    auto done = [&](int code) { dn.release(); dd.release(); df.release(); dr.release(); return code; };
+    const size_t b3 = (size_t)n * 3 * sizeof(float), b1 = (size_t)n * sizeof(float);
+    cudaError_t e = dn.ensure(b3);
+    if (e == cudaSuccess) e = dd.ensure(b1);
+    if (e == cudaSuccess) e = df.ensure(b3);
+    if (e == cudaSuccess) e = dr.ensure(b3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn.p, num, b3, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd.p, den, b1, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) { launch_division_selftest(c->stream, (const float*)dn.p, (const float*)dd.p, n, (float*)df.p, (float*)dr.p); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_fast, df.p, b3, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_ref, dr.p, b3, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(c, ROMIS_ERR_CUDA, std::string("romis_selftest_division: ") + cudaGetErrorString(e)));
+    return done(ROMIS_OK);
+}
+
 extern "C" void* romis_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;

@@ -222,3 +222,41 @@ def test_light_table_dirty_tracking(renderer, oracle_factory):
     gimg = renderer.render_frame(feat, cam, W, H, True, 8, 2)
     assert_bits_equal(gimg, oimg, "frame after the light table shrank")
     compare_stage("lights", "after shrink", renderer.reservoirs(abi.ROMIS_PASS_FINAL), orc.reservoirs(abi.ROMIS_PASS_FINAL))
+
+
+@pytest.mark.gpu
+def test_shared_reciprocal_division():
+    """div3_shared (three divisions by one denominator behind one refined reciprocal, csrc/device_common.cuh) returns the bits of
+    the plain IEEE division for every operand: random bit patterns (all exponents, subnormals, infinities, NaNs), the ranges the
+    shading produces, exact zeros of both signs, operands on the edges of the fast path's exponent window, near-overflow quotients."""
+    from romis_b200.api import RestirRenderer
+    rng = np.random.default_rng(11)
+    r = RestirRenderer(0)
+    n = 1 << 22
+
+    def check(num, den, what):
+        fast, ref = r.selftest_division(num, den)
+        same = fast.view(np.uint32) == ref.view(np.uint32)
+        both_nan = np.isnan(fast) & np.isnan(ref)
+        bad = ~(same | both_nan)
+        assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} quotients differ, first at {np.argwhere(bad)[0]}"
+
+    bits = lambda k: rng.integers(0, 1 << 32, size=k, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    check(bits(3 * n).reshape(n, 3), bits(n), "random bit patterns")
+    check(bits(3 * n).reshape(n, 3), np.abs(bits(n)), "random bit patterns, positive denominators")
+    # what computeShading divides: radiance-like numerators (some channels exactly zero), squared distances
+    num = (rng.random((n, 3), dtype=np.float32) ** 4 * np.float32(50.0)).astype(np.float32)
+    num[rng.random((n, 3)) < 0.2] = 0.0
+    num[rng.random((n, 3)) < 0.01] = -0.0
+    den = (rng.random(n, dtype=np.float32) * np.float32(30.0) + np.float32(1e-4)).astype(np.float32) ** 2
+    check(num, den, "shading range")
+    check(-num, den, "shading range, negative numerators")
+    # exponent edges of the fast path (2^-60 .. 2^60 numerators, 2^-40 .. 2^40 denominators), a binade either side
+    e_num = rng.integers(-63, 64, size=(n, 3)); e_den = rng.integers(-43, 44, size=n)
+    mant = lambda shape: (1.0 + rng.random(shape)).astype(np.float32)
+    check(np.ldexp(mant((n, 3)), e_num).astype(np.float32), np.ldexp(mant(n), e_den).astype(np.float32), "window edges")
+    # quotients next to overflow / underflow
+    e_num = rng.integers(60, 128, size=(n, 3)); e_den = rng.integers(-60, -30, size=n)
+    check(np.ldexp(mant((n, 3)), e_num).astype(np.float32), np.ldexp(mant(n), e_den).astype(np.float32), "towards overflow")
+    check(np.ldexp(mant((n, 3)), -e_num).astype(np.float32), np.ldexp(mant(n), -e_den).astype(np.float32), "towards underflow")
+    r.close()

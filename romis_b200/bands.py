@@ -201,7 +201,7 @@ class BandedRenderer:
         self.edges = balanced_band_edges(hits + miss_cost * (W - hits), self.world_size, max(radius, 1))
         self._height = None
 
-    def calibrate(self, features, camera, W: int, H: int, seed: int = 1, rounds: int = 6, frames: int = 3, tolerance: float = 0.03):
+    def calibrate(self, features, camera, W: int, H: int, seed: int = 1, rounds: int = 8, frames: int = 4, tolerance: float = 0.01):
         """Measured refinement of the band edges (static camera): render a few frames, take every rank's own compute time
         (all pass kernels; the wait for the neighbours' halo rows is timed separately) and recut with `refine_band_edges`;
         up to `rounds` times, until the slowest band is within `tolerance` of the mean, and the best cut seen is kept.  Cost

@@ -123,14 +123,6 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_kernel(SceneD
 // first: each waits until the neighbour's token of the PREVIOUS stage has arrived (its boundary rows are in my halo, and it has
 // finished reading the halo rows of the buffer I am about to write into), runs, stores its rows twice (here and into the
 // neighbour's halo) and the last such block of an edge publishes this stage's token.  Interior row groups never wait.
-__device__ __forceinline__ void halo_spin(const uint32_t* f, uint32_t token, uint32_t* err) {
-    const volatile uint32_t* vf = f;
-    const long long t0 = clock64();
-    while ((int32_t)(*vf - token) < 0) {
-        __nanosleep(64);
-        if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }
-    }
-}
 template <int NT, bool UNBIASED, bool ES>
 __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, ResBuf out, int pass, HaloDev hd, FineDev fd) {
     int by = (int)blockIdx.y;

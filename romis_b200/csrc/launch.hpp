@@ -22,7 +22,7 @@ void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, c
 void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
                     float* wsum = nullptr, float* chosen = nullptr);
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
-                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out, const FineDev& fd);
+                     const ResBuf& cur, const ResBuf& prev, const ResBuf& out, const FineDev& fd, const HaloDev& hd);
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                     const ResBuf& in, const ResBuf& out, int pass, const FineDev& fd);
 void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,

@@ -73,6 +73,7 @@ struct romis_ctx {
     FrameDev fr{};
     int next_pass = 0;
     int n_launches = 0;
+    bool stage0_pushed = false;         // the temporal pass of this frame stored its boundary rows into the neighbours' halos itself
 
     // peer-mapped halos (one process per GPU; see romis_peer_attach)
     // multi-device context (romis_create with n_devices > 1): one child context per device, each renders a row band of the
@@ -703,6 +704,8 @@ static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, in
     return ROMIS_OK;
 }
 
+static HaloDev halo_for_stage0(romis_ctx* c, int out, const dim3& grid, const dim3& block);
+
 extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const romis_camera* cam, int W, int H,
                                  int history_valid, const romis_rng* rng) {
     if (!c) return ROMIS_ERR_INVALID;
@@ -741,6 +744,7 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 1, 0));
 
+    c->stage0_pushed = false;
     c->fine_src = -1;           // which stage's counters the next pass may wait on (-1: wait for the whole previous kernel)
     // 2. initial RIS (+ visibility reuse)
     launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
@@ -751,7 +755,9 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
 
     // 3. temporal reuse (in place on w0; reads the history)
     if (f->temporalReuse && c->history_valid) {
-        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0), fine_for(c, -1, 0, 0));
+        HaloDev hd; std::memset(&hd, 0, sizeof hd);
+        if ((c->peer[0].on || c->peer[1].on) && f->spatialReuse && f->spatialResamplingPasses > 0) { hd = halo_for_stage0(c, w0, gOwn, kBlockS); c->stage0_pushed = true; }
+        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0), fine_for(c, -1, 0, 0), hd);
         if (fine_enabled(c)) c->fine_src = 0;
         c->n_launches++;
         RCHECK(c, cudaGetLastError());
@@ -807,6 +813,31 @@ static int peer_push_stage0(romis_ctx* c, int in) {
                      nullptr, nullptr, my + 4, (unsigned int*)(my + 5));
     RCHECK(c, cudaGetLastError());
     return ROMIS_OK;
+}
+
+// The same stage 0 done by the temporal pass itself (k_temporal.cu): its blocks within `radius` rows of an edge store their rows
+// into the neighbours' halo rows of `out` as well, after the neighbours' last token of the previous frame, and publish the stage
+// token.  Used whenever the temporal pass runs; the copy kernel above remains for frames without one.
+static HaloDev halo_for_stage0(romis_ctx* c, int out, const dim3& grid, const dim3& block) {
+    HaloDev hd; std::memset(&hd, 0, sizeof hd);
+    uint32_t* my = (uint32_t*)c->flags.p;
+    const int r = (int)c->fr.f.spatialResampleRadius, rows = c->y1 - c->y0, bh = (int)block.y, nby = (int)grid.y;
+    const int nlo = std::min(nby, (r + bh - 1) / bh), gh0 = std::max(0, (rows - r) / bh);
+    for (int e = 0; e < 2; e++) {
+        const romis_ctx::Peer& p = c->peer[e];
+        if (!p.on) continue;
+        hd.peer_out[e] = p.res[out];
+        hd.peer_stride[e] = p.row_stride; hd.peer_ey0[e] = p.ey0;
+        hd.wait_flag[e] = my + e;
+        hd.sig_flag[e] = p.flags + (e == 0 ? 1 : 0);
+        hd.edge_blocks[e] = (unsigned int)((e == 0 ? nlo : nby - gh0) * (int)grid.x);
+    }
+    hd.counter = (unsigned int*)(my + 6);
+    hd.err = my + 4;
+    hd.wait_token = c->epoch; hd.token = ++c->epoch;
+    hd.push = 1;
+    hd.r = r;
+    return hd;
 }
 
 // Fused halo exchange of spatial pass `pass` (HaloDev, k_spatial.cu spatial_halo_kernel): stage tokens are a running count
@@ -975,7 +1006,7 @@ extern "C" int romis_frame_spatial_pass(romis_ctx* c, int pass) {
     const FineDev fd = fine_for(c, c->fine_src, fine_out ? 1 + pass : -1, (int)c->fr.f.spatialResampleRadius);
     c->fine_src = fine_out ? 1 + pass : -1;
     if (c->peer[0].on || c->peer[1].on) {
-        if (pass == 0) { int prc = peer_push_stage0(c, in); if (prc) return prc; c->n_launches++; RCHECK(c, mark(c, 6, pass)); }
+        if (pass == 0 && !c->stage0_pushed) { int prc = peer_push_stage0(c, in); if (prc) return prc; c->n_launches++; RCHECK(c, mark(c, 6, pass)); }
         const HaloDev hd = halo_for_pass(c, out, pass, gOwn, kBlock);
         launch_spatial_halo(c->stream, gOwn, kBlock, c->N, c->fr.f.unbiasedCombination != 0, c->sc, c->fr, gbuf(c), resbuf(c, in), resbuf(c, out), pass, hd, fd);
     } else

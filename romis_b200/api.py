@@ -150,6 +150,32 @@ class PinnedImage:
             load_library().romis_host_free(self.ptr); self.ptr = None
 
 
+class SharedImage:
+    """ONE float RGB image in Screen::pixels() layout that several processes (one per GPU) fill together: POSIX shared memory,
+    page-locked in every process that attaches (romis_host_register), so each band's rows arrive by asynchronous DMA over that
+    GPU's own PCIe link and the caller -- the creating process -- ends up with the whole frame in one buffer."""
+
+    def __init__(self, H, W, name=None):
+        from multiprocessing import shared_memory
+        self.nbytes = H * W * 3 * 4
+        self.owner = name is None
+        self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes) if self.owner else shared_memory.SharedMemory(name=name)
+        self.name = self.shm.name
+        self.array = np.ndarray((H, W, 3), np.float32, buffer=self.shm.buf)
+        self.ptr = self.array.ctypes.data
+        if load_library().romis_host_register(self.ptr, self.nbytes) != 0:
+            raise RomisError("romis_host_register failed on the shared image")
+
+    def free(self):
+        if self.shm is not None:
+            load_library().romis_host_unregister(self.ptr)
+            self.array = None
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+            self.shm = None
+
+
 class RestirRenderer:
     """One context = one GPU (optionally one row band of the frame); with a list of devices: one context driving one row band
     per GPU from this single process (romis_create with n_devices > 1)."""

@@ -271,19 +271,18 @@ def mis_pass_bytes(mode: str, N: int, K1: int):
 
 
 def run_mis(args, mode, rank, world):
-    """R-MIS / R-OMIS frames on one GPU (these modes are not sharded: --gpus N > 1 would be N replicas, not run here)."""
+    """R-MIS / R-OMIS frames.  N > 1 (torchrun, one process per GPU): row bands of equal cost by the per-row hit profile; a band
+    renders its halo rows itself (no collective), every rank's rows land in one shared host image."""
     import torch
     from romis_b200.api import PinnedImage, RestirRenderer
     from romis_b200.scene import RmisParams
-    if world > 1:
-        if rank == 0:
-            print(json.dumps({"impl": "ours", "config": {"workload": mode}, "unavailable": "R-MIS / R-OMIS frames are not sharded: run with --gpus 1"}), flush=True)
-        return
     label, scene, W, H, feat, cam = workload("c2")
     label = label.split(" M=")[0] + f" {'R-MIS equal weights' if mode == 'rmis' else 'R-OMIS direct estimator'}, 5 iterations, M=32 N=2 k=5 r=10, similar neighbours, visibility reuse"
     rp = RmisParams()                                   # the reference's defaults (common.h:110-121)
     K1 = feat.numNeighboursToSample + 1; N = feat.numSamplesInReservoir
     if args.impl == "reference":
+        if rank != 0:
+            return                                      # rank 0 alone runs the CPU reference
         from oracle.pyoracle import RefLib
         ref = RefLib(); ref.set_scene(scene); ref.set_mis_timing(True)
         div = 8
@@ -304,19 +303,63 @@ def run_mis(args, mode, rank, world):
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
                           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
-    torch.cuda.set_device(0)
-    r = RestirRenderer(0); r.upload_scene(scene)
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    edges = None
+    if world > 1:
+        import torch.distributed as dist
+        from romis_b200.api import SharedImage
+        from romis_b200.bands import balanced_band_edges
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    r = RestirRenderer(local_rank); r.upload_scene(scene)
+    if world > 1:
+        hits = r.row_hit_counts(cam, W, H).astype("float64")
+        edges = balanced_band_edges(hits + 0.04 * (W - hits), world, 1)
+        r.set_band(edges[rank], edges[rank + 1])
+        names = [None]
+        if rank == 0:
+            host_img = SharedImage(H, W); names[0] = host_img.name
+        dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            host_img = SharedImage(H, W, name=names[0])
+    else:
+        host_img = PinnedImage(H, W)
     render = r.render_frame_rmis if mode == "rmis" else r.render_frame_romis
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if world > 1 and not args.equal_rows:
+        # measured refinement of the cut (untimed; the same routine as the ReSTIR bands, romis_b200/bands.py): a band's cost is
+        # not its hit count alone
+        from romis_b200.bands import refine_band_edges
+        best = None
+        for _ in range(5):
+            render(feat, rp, cam, W, H, SEED, 0, want_image=False)
+            render(feat, rp, cam, W, H, SEED, 1, want_image=False)
+            times = [None] * world
+            dist.all_gather_object(times, float(r.timings().total_ms))
+            if best is None or max(times) < best[0]:
+                best = (max(times), list(edges))
+            if max(times) <= 1.01 * sum(times) / world:
+                break
+            edges = refine_band_edges(edges, times, hits + 0.04 * (W - hits), 1, fixed_frac=0.1)
+            r.set_band(edges[rank], edges[rank + 1])
+        edges = best[1]
+        r.set_band(edges[rank], edges[rank + 1])
 
     def run_steps(n, first, host=False, stage=False):
         r.set_stage_timing(stage)
         tot = 0.0; acc = {}
         for i in range(n):
             flush.fill_(i & 0xff); torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             if host:
                 scene.lights["c0"][0, 0] = np.float32(0.65 + 1e-4 * ((first + i) % 7)); r.upload_lights(scene.lights)
-                t0 = time.perf_counter(); render(feat, rp, cam, W, H, SEED, first + i, want_image=True); tot += 1e3 * (time.perf_counter() - t0)
+                t0 = time.perf_counter(); render(feat, rp, cam, W, H, SEED, first + i, out=host_img.array)
+                if world > 1:
+                    dist.barrier()                  # the frame is there when every band is
+                tot += 1e3 * (time.perf_counter() - t0)
             else:
                 render(feat, rp, cam, W, H, SEED, first + i, want_image=False)
                 t = r.timings(); tot += t.total_ms
@@ -332,6 +375,25 @@ def run_mis(args, mode, rank, world):
     stage_ms, st = run_steps(args.steps, args.warmup + args.steps, stage=True)
     e2e_ms, _ = run_steps(args.steps, args.warmup + 2 * args.steps, host=True)
     clk = clocks.stop()
+    one_image = None
+    if world > 1:
+        if rank == 0:
+            host_img.array[...] = np.float32(np.nan)
+        dist.barrier()
+        run_steps(1, args.warmup + 3 * args.steps, host=True)
+        if rank == 0:
+            one_image = bool(not np.isnan(host_img.array).any())
+        t = torch.tensor([dev_ms, e2e_ms, stage_ms] + [st.get(k, 0.0) for k in ("primary_ms", "neighbours_ms", "initial_ms", "gather_ms", "resolve_ms")],
+                         dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = [float(a) for a in t.tolist()]
+        dev_ms, e2e_ms, stage_ms = v[:3]
+        for k, a in zip(("primary_ms", "neighbours_ms", "initial_ms", "gather_ms", "resolve_ms"), v[3:]):
+            st[k] = a
+        dist.barrier()
+        if rank != 0:
+            host_img.free(); r.close(); dist.destroy_process_group()
+            return
     ms = dev_ms / args.steps; fps = 1e3 / ms
     iters = rp.maxIterationsMIS
     peak, peak_src = measured_peak_gbs()
@@ -339,18 +401,19 @@ def run_mis(args, mode, rank, world):
     gb = mis_pass_bytes(mode, N, K1)
     ach = gb * W * H / (g_ms * 1e-3) / 1e9
     kern = "rmis_gather_kernel" if mode == "rmis" else "romis_accumulate_kernel"
-    line = {"metric": f"{mode.upper()} frames/s", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": f"{mode.upper()} frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
-            "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the timed region)", "sharding": "single GPU"},
+            "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the timed region)",
+                       "sharding": "single GPU" if world == 1 else f"{world} row bands, halo rows re-rendered per band (no collective)", "band_edges": edges},
             "gcandidates_per_s": W * H * feat.initialLightSamples * iters * fps / 1e9,
             "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": "frames/s", "h2d_bytes_per_step": int(6 * 16 * len(scene.lights) + 256), "d2h_bytes_per_step": int(W * H * 12),
-                    "note": "host wall clock around romis_render_frame_" + mode + " with a host image; lights re-uploaded (one edited) per frame"},
+                    "note": "host wall clock around romis_render_frame_" + mode + " with a host image; lights re-uploaded (one edited) per frame", "one_host_image": one_image},
             "gpu_launches": int(st["launches"] * args.steps), "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_px_per_iteration": gb,
                          "note": "issue-bound like the ReSTIR passes: " + ("(k+1) N shading evaluations + shadow rays" if mode == "rmis" else "(k+1)^2 N target-pdf evaluations") + " per pixel per iteration",
                          "stages_ms_per_frame": {k: round(v / args.steps, 4) for k, v in st.items() if k.endswith("_ms")}}}
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         from oracle.pyoracle import RefLib
         ref = RefLib(); ref.set_scene(scene); ref.set_mis_timing(True)
         w, h = W // 8, H // 8; scale = (w * h) / float(W * H)
@@ -363,6 +426,9 @@ def run_mis(args, mode, rank, world):
         line["cpu_baseline"] = {"value": 1e3 / cms, "unit": "frames/s", "cores": host_cores(), "kind": "reference",
                                 "sample": f"{len(ts)} frames at {w}x{h} ({scale:.4f} of the pixels, same scene/Features), median, scaled by pixel count"}
     print(json.dumps(line), flush=True)
+    host_img.free(); r.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -264,25 +264,27 @@ class RestirRenderer:
         return dev.value
 
     def render_frame_rmis(self, features: Features, rmis: RmisParams, camera, W: int, H: int, seed: int, frame: int,
-                          want_image: bool = True):
+                          want_image: bool = True, out=None):
         """renderRMIS (reference src/rendering/render.cpp:64-119): the R-MIS estimator, no temporal state.  Returns the
         float RGB image [H, W, 3] in Screen::pixels() layout, or None with want_image=False (image stays on the device)."""
         f = features.to_abi(); rp = rmis.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
-        out = np.zeros((H, W, 3), np.float32) if want_image else None
+        if out is None and want_image:
+            out = np.zeros((H, W, 3), np.float32)       # with a row band set (set_band) only the band's rows are written
         self._check(self.lib.romis_render_frame_rmis(self.ctx, C.byref(f), C.byref(rp), C.byref(cam), W, H, C.byref(r),
-                                                     out.ctypes.data if want_image else None))
+                                                     out.ctypes.data if out is not None else None))
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         self._rmis_k1 = features.numNeighboursToSample + 1
         return out
 
     def render_frame_romis(self, features: Features, rmis: RmisParams, camera, W: int, H: int, seed: int, frame: int,
-                           want_image: bool = True):
+                           want_image: bool = True, out=None):
         """renderROMIS (reference src/rendering/render.cpp:121-265), direct estimator.  Returns the float RGB image
         [H, W, 3] in Screen::pixels() layout, or None with want_image=False (image stays on the device)."""
         f = features.to_abi(); rp = rmis.to_abi(); cam = self._cam(camera, W, H); r = abi.romis_rng(seed, frame, 0)
-        out = np.zeros((H, W, 3), np.float32) if want_image else None
+        if out is None and want_image:
+            out = np.zeros((H, W, 3), np.float32)       # with a row band set (set_band) only the band's rows are written
         self._check(self.lib.romis_render_frame_romis(self.ctx, C.byref(f), C.byref(rp), C.byref(cam), W, H, C.byref(r),
-                                                      out.ctypes.data if want_image else None))
+                                                      out.ctypes.data if out is not None else None))
         self.W, self.H, self.N = W, H, features.numSamplesInReservoir
         self._rmis_k1 = features.numNeighboursToSample + 1
         return out

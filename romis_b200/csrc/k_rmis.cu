@@ -131,9 +131,11 @@ __device__ __forceinline__ void emit_class(const RmisWindow& w, bool cls, uint32
 // generateResampleIndicesGrid: indicesRandom (neighbour_selection.cpp:24-45) / indicesSimilarity (:47-105)
 __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, FrameDev fr, GBufDev g, RmisDev rm) {
     int x, y; thread_pixel<true>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += fr.y0;                                     // the band's own rows; the window below may reach into its halo rows
+    if (x >= fr.W || y >= fr.y1) return;
     const int k = (int)fr.f.numNeighboursToSample, r = (int)fr.f.spatialResampleRadius;
-    const size_t p = (size_t)y * fr.W + x;
+    const size_t p = (size_t)y * fr.W + x;          // R-MIS planes are indexed by the GLOBAL pixel, G-buffer and reservoirs by band row
+    const size_t lp = (size_t)(y - fr.ey0) * fr.W + x;
     uint32_t* col = rm.nb + p;
     romis_stream_key ek = romis_rng_stream(fr.seed, fr.frame, ROMIS_STAGE_RMIS_NEIGH, (uint32_t)p, ROMIS_STREAM_ENGINE);
     uint32_t ec = 0;
@@ -152,14 +154,14 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
         // classify the window (:59-72): one bit per window pixel, 32 pixels per mask word
         RmisWindow w;
         w.x0 = wx0; w.y0 = wy0; w.wx = wx1 - wx0 + 1; w.count = w.wx * (wy1 - wy0 + 1); w.own = (y - wy0) * w.wx + (x - wx0);
-        const float4 own = g.tn[p]; const uint32_t own_mesh = g.mesh[p];
+        const float4 own = g.tn[lp]; const uint32_t own_mesh = g.mesh[lp];
         const uint32_t own_gid = own_mesh == (uint32_t)sc.n_meshes ? 0u : own_mesh;    // a miss pixel keeps the value-initialised geometryId 0
         const bool sameGeometry = rm.p.neighbourSameGeometry != 0;
         const float maxDepthFrac = rm.p.neighbourMaxDepthDifferenceFraction, minNormalsDot = rm.p.neighbourMaxNormalAngleDifferenceRadians;
         uint32_t ns = 0, word = 0; int bit = 0, wi = 0;
         for (int ny = wy0; ny <= wy1; ny++) {
-            const float4* __restrict__ trow = g.tn + (size_t)ny * fr.W + wx0;
-            const uint32_t* __restrict__ mrow = g.mesh + (size_t)ny * fr.W + wx0;
+            const float4* __restrict__ trow = g.tn + (size_t)(ny - fr.ey0) * fr.W + wx0;
+            const uint32_t* __restrict__ mrow = g.mesh + (size_t)(ny - fr.ey0) * fr.W + wx0;
             _Pragma("unroll 3") for (int cx = 0; cx < w.wx; cx++) {
                 const bool s = are_similar_flat(sameGeometry, maxDepthFrac, minNormalsDot, (uint32_t)sc.n_meshes, own, own_gid, trow[cx], mrow[cx]);
                 word |= (s ? 1u : 0u) << bit;
@@ -190,12 +192,13 @@ __global__ void __launch_bounds__(256) rmis_neighbours_kernel(SceneDev sc, Frame
 }
 
 // Hit point and unit view vector of every pixel, once per frame (GBufDev::pv): exactly make_ctx's arithmetic.
-__global__ void __launch_bounds__(256) ctx_kernel(SceneDev sc, FrameDev fr, GBufDev g) {
+__global__ void __launch_bounds__(256) ctx_kernel(SceneDev sc, FrameDev fr, GBufDev g, int row0, int row1) {
     int x, y; thread_pixel<false>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += row0;                                      // band rows plus halo rows
+    if (x >= fr.W || y >= row1) return;
     GBufDev g0 = g; g0.pv = nullptr;
     const PixCtx c = make_ctx<false>(sc, fr, g0, x, y);
-    const size_t p = (size_t)y * fr.W + x;
+    const size_t p = (size_t)(y - fr.ey0) * fr.W + x;      // like the G-buffer (make_ctx<true> reads it back so)
     g.pv[2 * p] = make_float4(c.P.x, c.P.y, c.P.z, 0.0f);
     g.pv[2 * p + 1] = make_float4(c.Vv.x, c.Vv.y, c.Vv.z, 0.0f);
 }
@@ -205,7 +208,8 @@ __global__ void __launch_bounds__(256) ctx_kernel(SceneDev sc, FrameDev fr, GBuf
 template <int NT>
 __global__ void __launch_bounds__(256, ROMIS_MINB_GATHER) rmis_gather_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
     int x, y; thread_pixel<false>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
     const size_t p = (size_t)y * fr.W + x;
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_GATHER) rmis_gather_kernel(Sce
         // sample) and zeroed W when it was blocked (light.cpp:86-87), so W != 0 below says "visible" without a second ray.
         const bool own_checked = fr.f.initialSamplesVisibilityCheck != 0 && q[a] == q[0];
         _Pragma("unroll 1") for (int j = 0; j < N; j++) {
-            const uint4 rec = res_rec(in, qy, j)[qx];
+            const uint4 rec = res_rec(in, qy - fr.ey0, j)[qx];
             const float Wj = __uint_as_float(rec.w);
             // W == 0 contributes (+-0) whatever the weight and the visibility: the sum keeps its bits
             if (Wj == 0.0f) continue;
@@ -253,7 +257,8 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_GATHER) rmis_gather_kernel(Sce
 // combineToScreen (render_utils.cpp:68-85): average over the iterations, tone map, Screen layout
 __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb) {
     int x, y; thread_pixel<false>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
     const float4 acc = rm.acc[(size_t)y * fr.W + x];
     v3 color = div3(V3(acc.x, acc.y, acc.z), (float)rm.p.maxIterationsMIS);
     if (fr.f.enableToneMapping) color = tone_map(color, fr.f);                      // tone_mapping.cpp:8-11
@@ -276,7 +281,8 @@ __global__ void __launch_bounds__(256) rmis_combine_kernel(FrameDev fr, RmisDev 
 template <int NT, bool PROG>
 __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf in, RmisDev rm) {
     int x, y; thread_pixel<false>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
     constexpr int CAP = SubRes<NT>::CAP;
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const int K1 = rm.K1;
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
         const int by = (int)(q[a] >> 16), bx = (int)(q[a] & 0xffffu);
         const size_t bp = (size_t)by * fr.W + bx;
         ROMIS_FOR_SUB(j, NT, N) {
-            invM[a][j] = 1.0f / (float)res_m(in, by, j)[bx];
+            invM[a][j] = 1.0f / (float)res_m(in, by - fr.ey0, j)[bx];
             wRest[a][j] = rm.wsum[(size_t)j * rm.plane + bp] - rm.chosen[(size_t)j * rm.plane + bp];
         }
     }
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
         const int ay = (int)(q[a] >> 16), ax = (int)(q[a] & 0xffffu);
         v3 spos[CAP], scol[CAP];
         ROMIS_FOR_SUB(j, NT, N) {
-            const uint4 rec = res_rec(in, ay, j)[ax];
+            const uint4 rec = res_rec(in, ay - fr.ey0, j)[ax];
             light_sample<true>(sc, rec.x, __uint_as_float(rec.y), __uint_as_float(rec.z), spos[j], scol[j]);
         }
         // The samples shaded at this pixel (:184-186), once: the value is also distribution 0's target pdf (plane 0 of the
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
                 else { imj = im[j]; wrj = wr[j]; }
                 float pdf;
                 if (own) pdf = c.miss ? 0.0f : length3(shade[j]);
-                else if (stored) pdf = res_pdf(in, by, j)[bx];
+                else if (stored) pdf = res_pdf(in, by - fr.ey0, j)[bx];
                 else pdf = target_pdf(cb, es, spos[j], scol[j]);
                 if (pdf != 0.0f) {                                                  // render_utils.cpp:248-256
                     const float mock = pow2L ? pdf * nLights : pdf / invPdf;
@@ -408,7 +414,8 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
 // alphas_only: the progressive estimator's per-iteration update of the alpha vectors (:160-164) instead of the image.
 __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb, int alphas_only) {
     int x, y; thread_pixel<false>(x, y);
-    if (x >= fr.W || y >= fr.H) return;
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
     const int K1 = rm.K1;
     const size_t p = (size_t)y * fr.W + x;
     float A[ROMIS_COD_MAX * ROMIS_COD_MAX], b[ROMIS_COD_MAX], xs[ROMIS_COD_MAX];
@@ -432,8 +439,8 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
     rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
 }
 
-void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g) {
-    ctx_kernel<<<grid, block, 0, s>>>(sc, fr, g);
+void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1) {
+    ctx_kernel<<<grid, block, 0, s>>>(sc, fr, g, row0, row1);
 }
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm) {
     rmis_neighbours_kernel<<<grid, block, 0, s>>>(sc, fr, g, rm);
@@ -446,7 +453,7 @@ void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const
     else { ROMIS_DISPATCH_N(N, (romis_accumulate_kernel<NT, false><<<grid, block, 0, s>>>(sc, fr, g, in, rm))); }
 }
 void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb, bool alphas_only) {
-    dim3 b(32, 4), gr((fr.W + 31) / 32, (fr.H + 3) / 4);
+    dim3 b(32, 4), gr((fr.W + 31) / 32, (fr.y1 - fr.y0 + 3) / 4);
     romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb, alphas_only ? 1 : 0);
 }
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {

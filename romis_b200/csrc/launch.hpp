@@ -29,7 +29,7 @@ void launch_spatial_halo(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbi
                          const ResBuf& in, const ResBuf& out, int pass, const HaloDev& hd, const FineDev& fd);
 void launch_shade(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, float* rgb,
                   const FineDev& fd);
-void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g);
+void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1);
 void launch_rmis_neighbours(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const RmisDev& rm);
 void launch_rmis_gather(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);
 void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& in, const RmisDev& rm);

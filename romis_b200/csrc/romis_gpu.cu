@@ -671,11 +671,11 @@ static FineDev fine_for(romis_ctx* c, int consume, int produce, int reach) {
 
 // (Re)allocates the per-frame buffers for (W, H, N, band, halo).  A change of resolution, band or N drops the temporal
 // history (the reference would read out of bounds).
-static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, int H) {
+static int ensure_frame_buffers(romis_ctx* c, const romis_features* f, int W, int H, int min_halo = 0) {
     const int N = (int)f->numSamplesInReservoir;
     int y0 = 0, y1 = H;
     if (c->band_y1 > c->band_y0) { y0 = c->band_y0; y1 = c->band_y1; if (y1 > H) return fail(c, ROMIS_ERR_INVALID, "band exceeds the image height"); }
-    const int halo = f->spatialReuse ? (int)f->spatialResampleRadius : 0;
+    const int halo = std::max(min_halo, f->spatialReuse ? (int)f->spatialResampleRadius : 0);
     if (W != c->W || H != c->H || N != c->N || halo > c->halo || y0 != c->y0 || y1 != c->y1) {
         if (c->peer[0].on || c->peer[1].on || c->exported)
             return fail(c, ROMIS_ERR_STATE, "frame geometry changed after romis_peer_export: detach, prepare, export and attach again");
@@ -1275,7 +1275,6 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     if (!rp) return fail(c, ROMIS_ERR_INVALID, "null rmis parameters");
     int rc = validate(c, f, cam, W, H, rng);
     if (rc) return rc;
-    if (c->band_y1 > c->band_y0) return fail(c, ROMIS_ERR_INVALID, "row bands are not supported in R-MIS / R-OMIS mode");
     if (rp->maxIterationsMIS < 1) return fail(c, ROMIS_ERR_INVALID, "maxIterationsMIS must be >= 1");
     if (mode == 0 && rp->misWeightRMIS > ROMIS_MIS_BALANCE) return fail(c, ROMIS_ERR_INVALID, "unhandled MIS weight type (render.cpp:99)");
     if (rp->neighbourSelectionStrategy == ROMIS_NEIGHBOURS_DISSIMILAR)
@@ -1302,7 +1301,15 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
         }
     }
     RCHECK(c, cudaSetDevice(c->device));
-    if ((rc = ensure_frame_buffers(c, f, W, H))) return rc;
+    // Row bands (romis_set_band): a band needs the reservoirs and shading contexts of the pixels within the resample radius of its
+    // rows.  Everything those depend on is a function of the pixel alone (the random stream is keyed by the global pixel), so a
+    // band simply renders its halo rows itself -- primary rays, contexts and every iteration's initial reservoirs over rows
+    // [y0 - r, y1 + r) -- instead of exchanging them: no collective, bit-identical to the undivided frame, (rows + 2 r) / rows of
+    // the initial-pass work.  Neighbour grid, gather / accumulation, solve and combine run over the band's own rows.
+    const int r_halo = (int)f->spatialResampleRadius;
+    if ((rc = ensure_frame_buffers(c, f, W, H, c->band_y1 > c->band_y0 ? r_halo : 0))) return rc;
+    if (c->peer[0].on || c->peer[1].on) return fail(c, ROMIS_ERR_STATE, "R-MIS / R-OMIS frames need no peer mapping: detach first");
+    const int hy0 = std::max(0, c->y0 - r_halo), hy1 = std::min(H, c->y1 + r_halo);       // rows rendered incl. halo (within ey0 .. ey1)
 
     const size_t px = (size_t)W * H;
     RCHECK(c, c->rmis_nb.ensure(px * K1 * sizeof(uint32_t)));
@@ -1337,26 +1344,27 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     fr.cam.qw = cam->quat[0]; fr.cam.qx = cam->quat[1]; fr.cam.qy = cam->quat[2]; fr.cam.qz = cam->quat[3];
     fr.cam.half_w = cam->half_width; fr.cam.half_h = cam->half_height;
     fr.f = *f; fr.seed = rng->seed; fr.frame = rng->frame;
-    fr.W = W; fr.H = H; fr.y0 = 0; fr.y1 = H; fr.ey0 = 0; fr.ey1 = H;
+    fr.W = W; fr.H = H; fr.y0 = c->y0; fr.y1 = c->y1; fr.ey0 = c->ey0; fr.ey1 = c->ey1;
 
     c->marks.clear(); c->n_launches = 0; c->timings_pending = true;
     std::memset(&c->last, 0, sizeof c->last);
     RCHECK(c, cudaEventRecord(c->ev_begin, c->stream));
     RCHECK(c, mark(c, 0, 0));
-    const dim3 grid = grid_for(W, H);
+    const dim3 grid = grid_for(W, c->y1 - c->y0);           // the band's own rows
     const int work = (c->hist + 1) % 3;                     // a work buffer: the ReSTIR history stays untouched
     GBufDev g = gbuf(c); g.pv = (float4*)c->rmis_pv.p;
-    const dim3 gridS = grid_for(W, H, kBlockS);
-    launch_primary(c->stream, gridS, kBlockS, c->sc, fr, g, 0, H);                          // render.cpp:68 / :125
-    launch_ctx(c->stream, gridS, kBlockS, c->sc, fr, g);
+    const dim3 gridS = grid_for(W, c->y1 - c->y0, kBlockS), gridH = grid_for(W, hy1 - hy0, kBlockS);       // own rows / with halo rows
+    FrameDev frH = fr; frH.y0 = hy0; frH.y1 = hy1;          // the initial pass also covers the halo rows
+    launch_primary(c->stream, gridH, kBlockS, c->sc, fr, g, hy0, hy1);                     // render.cpp:68 / :125
+    launch_ctx(c->stream, gridH, kBlockS, c->sc, fr, g, hy0, hy1);
     RCHECK(c, mark(c, 1, 0));
     launch_rmis_neighbours(c->stream, grid, kBlock, c->sc, fr, g, rm);                // :69 / :126
     RCHECK(c, mark(c, 7, 0));
     c->n_launches += 3;
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
-        fr.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm.wsum, rm.chosen);     // :74 / :143
+        fr.initial_stage = frH.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
+        launch_initial(c->stream, gridH, kBlockS, c->N, c->sc, frH, g, resbuf(c, work), rm.wsum, rm.chosen);    // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164
@@ -1375,7 +1383,10 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, cudaEventRecord(c->ev_end, c->stream));
-    if (out_rgb) RCHECK(c, cudaMemcpyAsync(out_rgb, c->rgb.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (out_rgb) {          // band rows [y0, y1) are image rows [H - y1, H - y0) of the flipped Screen layout: one contiguous range
+        const size_t off = (size_t)(H - c->y1) * W * 3, cnt = (size_t)(c->y1 - c->y0) * W * 3;
+        RCHECK(c, cudaMemcpyAsync(out_rgb + off, (const float*)c->rgb.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
     RCHECK(c, cudaStreamSynchronize(c->stream));
     return ROMIS_OK;
 }

@@ -106,9 +106,33 @@ def test_rmis_error_paths(renderer):
         renderer.render_frame_rmis(Features(), RmisParams(misWeightRMIS=7), cam, 16, 16, 1, 0)
     with pytest.raises(RomisError):
         renderer.render_frame_rmis(Features(spatialResampleRadius=31), RmisParams(), cam, 16, 16, 1, 0)
-    renderer.set_band(0, 8)
+    renderer.set_band(0, 24)                        # a band beyond the image
     try:
         with pytest.raises(RomisError):
             renderer.render_frame_rmis(Features(), RmisParams(), cam, 16, 16, 1, 0)
     finally:
         renderer.set_band(0, 0)
+
+
+@pytest.mark.parametrize("mode", ["rmis", "romis", "romis_progressive"])
+def test_mis_frames_as_row_bands_equal_the_whole_frame(mode, renderer):
+    """R-MIS / R-OMIS frames sharded into row bands (romis_set_band): a band renders its halo rows itself -- primary rays and
+    every iteration's initial reservoirs are functions of the pixel alone -- so the bands, assembled, equal the undivided frame
+    bit for bit, with uneven bands, bands of fewer rows than the radius apart from the image edge, and for all three estimators."""
+    scene = load_scene("CornellNightClub"); scene.lights = synthetic_lights(512, seed=3)
+    W, H = 192, 108
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    renderer.upload_scene(scene)
+    feat = Features(initialSamplesVisibilityCheck=True, numSamplesInReservoir=6 if mode == "romis_progressive" else 2)
+    rp = RmisParams(maxIterationsMIS=3, misWeightRMIS=abi.ROMIS_MIS_BALANCE, neighbourSelectionStrategy=abi.ROMIS_NEIGHBOURS_SIMILAR,
+                    useProgressiveROMIS=mode == "romis_progressive", progressiveUpdateMod=1)
+    render = renderer.render_frame_rmis if mode == "rmis" else renderer.render_frame_romis
+    renderer.set_band(0, 0)
+    whole = render(feat, rp, cam, W, H, 5, 2)
+    banded = np.full((H, W, 3), np.nan, np.float32)
+    for y0, y1 in ((0, 37), (37, 49), (49, 95), (95, H)):
+        renderer.set_band(y0, y1)
+        render(feat, rp, cam, W, H, 5, 2, out=banded)
+    renderer.set_band(0, 0)
+    assert not np.isnan(banded).any(), "rows left unwritten by the bands"
+    assert_bits_equal(banded, whole, f"{mode}: bands vs whole frame")

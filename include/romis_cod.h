@@ -34,11 +34,13 @@
 typedef struct romis_cod {
     int n, rank;
     int perm[ROMIS_COD_MAX];                    /* colsPermutation().indices() */
-    float qr[ROMIS_COD_MAX * ROMIS_COD_MAX];    /* column-major: R / T above the diagonal, Householder essentials below and right */
+    float qr[ROMIS_COD_MAX * ROMIS_COD_MAX];    /* column-major with leading dimension n (the first n*n floats are used: a thread of the
+                                                   GPU solve touches 144 bytes for k = 5 instead of 484): R / T above the diagonal,
+                                                   Householder essentials below and right */
     float hc[ROMIS_COD_MAX], zc[ROMIS_COD_MAX]; /* hCoeffs, zCoeffs */
 } romis_cod;
 
-#define ROMIS_QR(d, i, j) ((d)->qr[(j) * ROMIS_COD_MAX + (i)])
+#define ROMIS_QR(d, i, j) ((d)->qr[(j) * ld + (i)])     /* `ld` = the system's n, a local of every user */
 
 /* makeHouseholder on the vector {*c0, tail[0 .. len*stride)} (Householder.h:67-96): on return *c0 is untouched, the tail
  * holds the essential part, *tau and *beta are set. */
@@ -59,12 +61,13 @@ ROMIS_COD_HD void romis_make_householder(const float* c0p, float* tail, int len,
     }
 }
 
-ROMIS_COD_HD void romis_cod_compute(romis_cod* d, const float* A, int n) {
+/* The decomposition of the n x n matrix the caller has put into d->qr (column-major, leading dimension n), in place. */
+ROMIS_COD_HD void romis_cod_factor(romis_cod* d, int n) {
     const float eps = FLT_EPSILON;
+    const int ld = n;
     float normsUpdated[ROMIS_COD_MAX], normsDirect[ROMIS_COD_MAX];
     int transp[ROMIS_COD_MAX];
     d->n = n;
-    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) ROMIS_QR(d, i, j) = A[i * n + j];
     float maxNorm = 0.0f;
     for (int k = 0; k < n; k++) {
         float s = 0.0f;
@@ -130,7 +133,7 @@ ROMIS_COD_HD void romis_cod_compute(romis_cod* d, const float* A, int n) {
             if (k != rank - 1)
                 for (int i = 0; i <= k; i++) { float t = ROMIS_QR(d, i, k); ROMIS_QR(d, i, k) = ROMIS_QR(d, i, rank - 1); ROMIS_QR(d, i, rank - 1) = t; }
             float tau, beta;
-            romis_make_householder(&ROMIS_QR(d, k, rank - 1), &ROMIS_QR(d, k, rank), n - rank, ROMIS_COD_MAX, &tau, &beta);
+            romis_make_householder(&ROMIS_QR(d, k, rank - 1), &ROMIS_QR(d, k, rank), n - rank, ld, &tau, &beta);
             d->zc[k] = tau;
             ROMIS_QR(d, k, rank - 1) = beta;
             /* topRightCorner(k, n-rank+1).applyHouseholderOnTheRight(row(k).tail(n-rank)^T, tau)  (Householder.h:153-171) */
@@ -149,9 +152,17 @@ ROMIS_COD_HD void romis_cod_compute(romis_cod* d, const float* A, int n) {
     }
 }
 
+/* A is row-major n x n */
+ROMIS_COD_HD void romis_cod_compute(romis_cod* d, const float* A, int n) {
+    const int ld = n;
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) ROMIS_QR(d, i, j) = A[i * n + j];
+    romis_cod_factor(d, n);
+}
+
 /* x = minimum-norm least-squares solution of A x = b (CompleteOrthogonalDecomposition::_solve_impl) */
 ROMIS_COD_HD void romis_cod_solve(const romis_cod* d, const float* b, float* x) {
     const int n = d->n > ROMIS_COD_MAX ? ROMIS_COD_MAX : d->n;
+    const int ld = n;
     const int rank = d->rank < 0 ? 0 : (d->rank > n ? n : d->rank);
     float c[ROMIS_COD_MAX] = {0.0f};
     if (rank == 0) { for (int i = 0; i < n; i++) x[i] = 0.0f; return; }

@@ -418,14 +418,21 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
     if (x >= fr.W || y >= fr.y1) return;
     const int K1 = rm.K1;
     const size_t p = (size_t)y * fr.W + x;
-    float A[ROMIS_COD_MAX * ROMIS_COD_MAX], b[ROMIS_COD_MAX], xs[ROMIS_COD_MAX];
+    float b[ROMIS_COD_MAX], xs[ROMIS_COD_MAX];
+    romis_cod cod;                                                                  // symmetric: straight into the factorisation's storage
+    bool any = false;
     for (int i = 0; i < K1; i++)                                                    // upper triangle stored, see the accumulation
-        for (int b = i; b < K1; b++) A[i * K1 + b] = A[b * K1 + i] = rm.tech[(size_t)(i * K1 + b) * rm.plane + p];
-    romis_cod cod;
-    romis_cod_compute(&cod, A, K1);
+        for (int b = i; b < K1; b++) {
+            const float t = rm.tech[(size_t)(i * K1 + b) * rm.plane + p];
+            cod.qr[i * K1 + b] = cod.qr[b * K1 + i] = t;
+            any |= t != 0.0f;
+        }
+    // An all-zero system (a pixel whose neighbourhood saw nothing: the misses, a quarter of the nightclub frame) has rank 0 -- every
+    // column norm, pivot and tau is 0, no diagonal entry exceeds the threshold 0 -- and the solution is x = 0 whatever b is.
+    if (any) romis_cod_factor(&cod, K1); else { cod.n = K1; cod.rank = 0; }
     float sum[3];
     for (int ch = 0; ch < 3; ch++) {
-        for (int i = 0; i < K1; i++) b[i] = rm.contrib[(size_t)(ch * K1 + i) * rm.plane + p];
+        if (any) for (int i = 0; i < K1; i++) b[i] = rm.contrib[(size_t)(ch * K1 + i) * rm.plane + p];
         romis_cod_solve(&cod, b, xs);
         if (alphas_only) { for (int i = 0; i < K1; i++) rm.alpha[(size_t)(ch * K1 + i) * rm.plane + p] = xs[i]; continue; }
         float s = 0.0f;

@@ -12,7 +12,9 @@ __global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) tempo
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
-    pdl_wait();                                     // `cur` comes from the kernel before this one
+    const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y), by1 = by0 + (int)blockDim.y;
+    // `cur` comes from the kernel before this one, the initial pass: its row groups of this block's rows (the whole kernel without counters)
+    fine_wait_rows(fd, y);
     pdl_launch_dependents();
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = ES || fr.f.enableShading != 0;
@@ -41,7 +43,6 @@ __global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) tempo
     res_take_counts(r, N);
     res_finish(r, N, sc, c, es);
     res_store(out, lrow, x, r, N);
-    const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y), by1 = by0 + (int)blockDim.y;
     fine_signal(fd, by0, by1);
     // Stage 0 of the frame's halo exchange (romis_gpu.cu "fused halo exchange"): the first spatial pass of the neighbouring bands
     // reads this pass's boundary rows, so the blocks that hold them store them a second time into the neighbours' halo rows --

@@ -80,6 +80,7 @@ struct romis_ctx {
     // frame; the parent only holds the children, the band edges and the error text (see "multi-device context" below)
     std::vector<romis_ctx*> kids;
     std::vector<int> g_edges; int g_active = 0, g_W = 0, g_H = 0, g_N = 0, g_halo = -1; bool g_wired = false;
+    std::vector<int> g_mis_edges; int g_mis_W = 0, g_mis_H = 0;     // band edges of R-MIS / R-OMIS frames (no minimum height)
 
     struct Peer {
         bool on = false;
@@ -657,15 +658,26 @@ static bool fine_enabled(const romis_ctx* c) {
     const long long blocks = (long long)((c->W + 31) / 32) * ((c->y1 - c->y0 + (int)kBlock.y - 1) / (int)kBlock.y);
     return blocks < 4LL * c->n_sms * ROMIS_MINB_SPATIAL;
 }
+// The link initial pass -> temporal pass (the temporal pass reads nothing but its own pixel's initial reservoir, and the tail of the
+// initial pass is the longest of the frame) has its own switch and warp-granular counting (fine_signal_rows / fine_wait_rows).
+// Measured on B200, C2: it LOSES -- counted per block (barrier + fence + atomic) the initial pass goes 0.970 -> 1.039 ms, because
+// the barrier keeps the registers of finished warps until the block's slowest warp is through; counted per warp (no barrier) it
+// goes 0.977 -> 1.101 ms: a __threadfence() per warp costs more than the tail it uncovers (full frame 2.469 -> 2.573 ms, 135-row
+// band 0.546 -> 0.585 ms).  Off unless ROMIS_FINE_INITIAL=1.
+#define ROMIS_FINE_STAGE_INITIAL (ROMIS_FINE_STAGES - 1)     // stage ids: 0 temporal, 1 + p spatial pass p (p <= 61), 64 initial
+static bool fine_initial_enabled(const romis_ctx* c) {
+    static const bool on = [] { const char* e = std::getenv("ROMIS_FINE_INITIAL"); return e && std::atoi(e) != 0; }();
+    return on && kBlockS.y == 4 && c->W;
+}
+static bool fine_link(const romis_ctx* c, int stage) { return stage == ROMIS_FINE_STAGE_INITIAL ? fine_initial_enabled(c) : fine_enabled(c); }
 static FineDev fine_for(romis_ctx* c, int consume, int produce, int reach) {
     FineDev fd; std::memset(&fd, 0, sizeof fd);
     fd.y0 = c->y0; fd.y1 = c->y1; fd.reach = reach;
     unsigned int* base = (unsigned int*)c->fine_ctr.p;
     fd.err = (uint32_t*)(base + (size_t)ROMIS_FINE_STAGES * c->fine_groups);
-    if (!fine_enabled(c)) return fd;
     const unsigned int per_group = (unsigned int)((c->W + 31) / 32);        // blocks are 32 pixels wide
-    if (consume >= 0) { fd.wait_ctr = base + (size_t)consume * c->fine_groups; fd.wait_target = per_group * c->fine_count[consume]; }
-    if (produce >= 0) { fd.sig_ctr = base + (size_t)produce * c->fine_groups; c->fine_count[produce]++; }
+    if (consume >= 0 && fine_link(c, consume)) { fd.wait_ctr = base + (size_t)consume * c->fine_groups; fd.wait_target = per_group * c->fine_count[consume]; }
+    if (produce >= 0 && fine_link(c, produce)) { fd.sig_ctr = base + (size_t)produce * c->fine_groups; c->fine_count[produce]++; }
     return fd;
 }
 
@@ -747,18 +759,22 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     c->stage0_pushed = false;
     c->fine_src = -1;           // which stage's counters the next pass may wait on (-1: wait for the whole previous kernel)
     // 2. initial RIS (+ visibility reuse)
-    launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
+    const bool with_temporal = f->temporalReuse && c->history_valid;
+    // its warps count themselves per row group for the temporal pass (fine_signal_rows / fine_wait_rows)
+    const bool count_initial = with_temporal && fine_initial_enabled(c);
+    launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), fine_for(c, -1, count_initial ? ROMIS_FINE_STAGE_INITIAL : -1, 0));
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 2, 0));
     if ((rc = capture_stage(c, ROMIS_PASS_INITIAL, w0))) return rc;
 
     // 3. temporal reuse (in place on w0; reads the history)
-    if (f->temporalReuse && c->history_valid) {
+    if (with_temporal) {
         HaloDev hd; std::memset(&hd, 0, sizeof hd);
         if ((c->peer[0].on || c->peer[1].on) && f->spatialReuse && f->spatialResamplingPasses > 0) { hd = halo_for_stage0(c, w0, gOwn, kBlockS); c->stage0_pushed = true; }
-        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0), fine_for(c, -1, 0, 0), hd);
-        if (fine_enabled(c)) c->fine_src = 0;
+        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0),
+                        fine_for(c, count_initial ? ROMIS_FINE_STAGE_INITIAL : -1, 0, 0), hd);
+        c->fine_src = fine_enabled(c) ? 0 : -1;
         c->n_launches++;
         RCHECK(c, cudaGetLastError());
         RCHECK(c, mark(c, 3, 0));
@@ -1267,10 +1283,9 @@ extern "C" int romis_render_frame_device(romis_ctx* c, const romis_features* f, 
 // R-MIS frame (renderRMIS, reference src/rendering/render.cpp:64-119)
 // ------------------------------------------------------------------------------------------------
 // mode 0 = R-MIS (renderRMIS, render.cpp:64-119), mode 1 = R-OMIS (renderROMIS, render.cpp:121-265)
-static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
-                            int W, int H, const romis_rng* rng, float* out_rgb) {
-    if (!c) return ROMIS_ERR_INVALID;
-    ROMIS_NOT_ON_GROUP(c, "R-MIS / R-OMIS frames are not sharded");
+// Everything of an R-MIS / R-OMIS frame but the final wait: the kernels and the read-back of the band's rows are in the stream.
+static int render_mis_enqueue(romis_ctx* c, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                              int W, int H, const romis_rng* rng, float* out_rgb, bool wired_ok = false) {
     if (c->in_frame) return fail(c, ROMIS_ERR_STATE, "frame in flight");
     if (!rp) return fail(c, ROMIS_ERR_INVALID, "null rmis parameters");
     int rc = validate(c, f, cam, W, H, rng);
@@ -1308,7 +1323,8 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     // the initial-pass work.  Neighbour grid, gather / accumulation, solve and combine run over the band's own rows.
     const int r_halo = (int)f->spatialResampleRadius;
     if ((rc = ensure_frame_buffers(c, f, W, H, c->band_y1 > c->band_y0 ? r_halo : 0))) return rc;
-    if (c->peer[0].on || c->peer[1].on) return fail(c, ROMIS_ERR_STATE, "R-MIS / R-OMIS frames need no peer mapping: detach first");
+    // (a multi-device context keeps its ReSTIR wiring: nothing of this frame touches a neighbour, and all devices are idle between frames)
+    if (!wired_ok && (c->peer[0].on || c->peer[1].on)) return fail(c, ROMIS_ERR_STATE, "R-MIS / R-OMIS frames need no peer mapping: detach first");
     const int hy0 = std::max(0, c->y0 - r_halo), hy1 = std::min(H, c->y1 + r_halo);       // rows rendered incl. halo (within ey0 .. ey1)
 
     const size_t px = (size_t)W * H;
@@ -1364,7 +1380,7 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = frH.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, gridH, kBlockS, c->N, c->sc, frH, g, resbuf(c, work), rm.wsum, rm.chosen);    // :74 / :143
+        launch_initial(c->stream, gridH, kBlockS, c->N, c->sc, frH, g, resbuf(c, work), FineDev{}, rm.wsum, rm.chosen);    // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164
@@ -1387,6 +1403,51 @@ static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, con
         const size_t off = (size_t)(H - c->y1) * W * 3, cnt = (size_t)(c->y1 - c->y0) * W * 3;
         RCHECK(c, cudaMemcpyAsync(out_rgb + off, (const float*)c->rgb.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
+    return ROMIS_OK;
+}
+
+// One caller, several GPUs: the R-MIS / R-OMIS frame as one row band per device (bands render their halo rows themselves, so the
+// devices exchange nothing), all enqueued from the caller's thread, then awaited.  When the context is already laid out for ReSTIR
+// frames of this geometry, the same bands are used and nothing is re-allocated: the temporal history of a ReSTIR sequence
+// survives R-MIS / R-OMIS frames in between, as the reference's previousFrameGrid does (render.cpp:268-280, main.cpp:164-165).
+static int group_render_mis(romis_ctx* g, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                            int W, int H, const romis_rng* rng, float* out_rgb) {
+    if (!f || !cam || !rng || W < 1 || H < 1) return fail(g, ROMIS_ERR_INVALID, "null features / camera / rng or empty frame");
+    const bool reuse = g->g_wired && g->g_W == W && g->g_H == H && g->g_N == (int)f->numSamplesInReservoir &&
+                       (int)f->spatialResampleRadius <= g->g_halo;
+    int rc = ROMIS_OK, active = g->g_active;
+    const std::vector<int>* edges = &g->g_edges;
+    if (!reuse) {
+        group_unwire(g);
+        active = std::max(1, std::min((int)g->kids.size(), H));
+        if (g->g_mis_edges.empty() || g->g_mis_W != W || g->g_mis_H != H || (int)g->g_mis_edges.size() != active + 1) {
+            std::vector<uint32_t> hits((size_t)H);
+            for (romis_ctx* k : g->kids) romis_set_band(k, 0, 0);
+            if ((rc = romis_row_hit_counts(g->kids[0], cam, W, H, hits.data()))) return group_fail(g, g->kids[0], rc);
+            std::vector<double> cost((size_t)H);
+            for (int y = 0; y < H; y++) cost[y] = hits[y] + 0.04 * (W - (double)hits[y]);
+            g->g_mis_edges = equal_cost_edges(cost, active, 1);
+            g->g_mis_W = W; g->g_mis_H = H;
+        }
+        edges = &g->g_mis_edges;
+        for (int i = 0; i < active; i++) if ((rc = romis_set_band(g->kids[i], (*edges)[i], (*edges)[i + 1]))) return group_fail(g, g->kids[i], rc);
+        g->g_active = active;
+    }
+    for (int i = 0; i < active; i++) if ((rc = render_mis_enqueue(g->kids[i], mode, f, rp, cam, W, H, rng, out_rgb, reuse))) return group_fail(g, g->kids[i], rc);
+    for (int i = 0; i < active; i++) {
+        romis_ctx* k = g->kids[i];
+        cudaSetDevice(k->device);
+        if (cudaStreamSynchronize(k->stream) != cudaSuccess) { k->err = "cudaStreamSynchronize"; return group_fail(g, k, ROMIS_ERR_CUDA); }
+    }
+    return ROMIS_OK;
+}
+
+static int render_mis_frame(romis_ctx* c, int mode, const romis_features* f, const romis_rmis_params* rp, const romis_camera* cam,
+                            int W, int H, const romis_rng* rng, float* out_rgb) {
+    if (!c) return ROMIS_ERR_INVALID;
+    if (!c->kids.empty()) return group_render_mis(c, mode, f, rp, cam, W, H, rng, out_rgb);
+    int rc = render_mis_enqueue(c, mode, f, rp, cam, W, H, rng, out_rgb);
+    if (rc) return rc;
     RCHECK(c, cudaStreamSynchronize(c->stream));
     return ROMIS_OK;
 }

@@ -83,18 +83,57 @@ def test_multi_device_context_equals_single_device_frame(n, oracle_factory):
 
 def test_multi_device_context_rejects_per_device_calls():
     from romis_b200.api import RestirRenderer, RomisError
-    from romis_b200.scene import Features, RmisParams
+    from romis_b200.scene import Features
     from cases import NIGHTCLUB_CAM
     from common import load_scene
     multi = RestirRenderer(_devices(2)); multi.upload_scene(load_scene("Cube"))
     try:
         for call in (lambda: multi.set_band(0, 8), lambda: multi.frame_begin(Features(), NIGHTCLUB_CAM, 16, 16, False, 1, 0),
-                     lambda: multi.render_frame_rmis(Features(), RmisParams(), NIGHTCLUB_CAM, 16, 16, 1, 0), lambda: multi.stream()):
+                     lambda: multi.stream()):
             with pytest.raises(RomisError, match="multi-device"):
                 call()
         multi.render_frame(Features(), NIGHTCLUB_CAM, 32, 32, False, 1, 0)     # tiny frame, radius 10: fewer bands than devices
     finally:
         multi.close()
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_multi_device_context_renders_mis_frames_and_keeps_the_restir_history(n):
+    """renderRMIS / renderROMIS through one context over n devices (one row band per device, halo rows rendered by the band itself)
+    equal the one-device frames bit for bit; and as in the reference, where previousFrameGrid outlives an R-MIS / R-OMIS frame
+    (render.cpp:268-280, main.cpp:164-165), a ReSTIR sequence interrupted by such frames continues from its temporal history."""
+    import numpy as np
+    from romis_b200 import abi
+    from romis_b200.api import RestirRenderer
+    from romis_b200.scene import Features, RmisParams, synthetic_lights
+    from cases import NIGHTCLUB_CAM
+    from common import assert_bits_equal, load_scene
+    scene = load_scene("CornellNightClub"); scene.lights = synthetic_lights(512, seed=3)
+    W, H = 176, 99
+    cam = NIGHTCLUB_CAM.to_abi(W, H)
+    feat = Features(spatialResamplingPasses=2, initialSamplesVisibilityCheck=True)
+    rp = RmisParams(maxIterationsMIS=2, misWeightRMIS=abi.ROMIS_MIS_BALANCE)
+    renderer = RestirRenderer(0); renderer.upload_scene(scene)
+    multi = RestirRenderer(_devices(n)); multi.upload_scene(scene)
+    try:
+        # before any ReSTIR frame: the context cuts bands for the R-MIS frame itself
+        assert_bits_equal(multi.render_frame_rmis(feat, rp, cam, W, H, 9, 0), renderer.render_frame_rmis(feat, rp, cam, W, H, 9, 0), "rmis, fresh context")
+        for fr in range(5):
+            if fr in (2, 4):      # laid out for ReSTIR by now: same bands, history untouched
+                assert_bits_equal(multi.render_frame_rmis(feat, rp, cam, W, H, 9, fr), renderer.render_frame_rmis(feat, rp, cam, W, H, 9, fr), f"rmis before frame {fr}")
+                assert_bits_equal(multi.render_frame_romis(feat, rp, cam, W, H, 9, fr), renderer.render_frame_romis(feat, rp, cam, W, H, 9, fr), f"romis before frame {fr}")
+            a = multi.render_frame(feat, cam, W, H, fr > 0, 31, fr)
+            b = renderer.render_frame(feat, cam, W, H, fr > 0, 31, fr)
+            assert_bits_equal(a, b, f"ReSTIR frame {fr} after R-MIS / R-OMIS frames")
+            g, o = multi.reservoirs(abi.ROMIS_PASS_FINAL), renderer.reservoirs(abi.ROMIS_PASS_FINAL)
+            for fld in ("light_id", "M", "W"):
+                assert_bits_equal(getattr(g, fld), getattr(o, fld), f"frame {fr} final {fld}")
+        # another radius than the layout was made for: own bands for the R-MIS frame, ReSTIR restarts
+        feat2 = Features(spatialResamplingPasses=2, initialSamplesVisibilityCheck=True, spatialResampleRadius=14)
+        assert_bits_equal(multi.render_frame_romis(feat2, rp, cam, W, H, 9, 7), renderer.render_frame_romis(feat2, rp, cam, W, H, 9, 7), "romis, radius 14")
+        assert_bits_equal(multi.render_frame(feat, cam, W, H, False, 31, 8), renderer.render_frame(feat, cam, W, H, False, 31, 8), "ReSTIR after re-layout")
+    finally:
+        multi.close(); renderer.close()
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libromis_dropin.so")), reason="oracle/_ref/libromis_dropin.so not built")

@@ -474,10 +474,16 @@ def main():
     if world > 1 and not args.equal_rows:
         # equal-COST bands: first cut from the primary-ray hit profile, then refined from measured per-band compute times
         # (untimed, before the warm-up; the camera of this workload is static)
-        br.balance(cam, W, H, feat.spatialResampleRadius if feat.spatialReuse else 0)
-        br.calibrate(feat, cam, W, H, seed=SEED)
+        # (C4, the orbit: cut for the mean over 8 cameras along the path and left alone -- no row changes owner mid-sequence)
+        path = [camera_for_frame(args.config, cam, f) for f in range(0, 64, 8)] if args.config == "c4" else cam
+        br.balance(path, W, H, feat.spatialResampleRadius if feat.spatialReuse else 0)
     N = feat.numSamplesInReservoir
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+    if world > 1 and not args.equal_rows:
+        def cold_l2():                  # the timed steps start from a flushed L2: so do the calibration's frames
+            with torch.cuda.stream(br.stream):
+                flush.fill_(1)
+        br.calibrate(feat, path, W, H, seed=SEED, before_frame=cold_l2)
 
     def barrier():
         if world > 1:
@@ -636,7 +642,8 @@ def main():
             "data": "synthetic", "impl": "ours",
             "config": {"workload": label, "width": W, "height": H, "seed": SEED, "l2": "256 MiB memset before every step (outside the step's events)",
                        "sharding": (f"{world} row bands, halo = radius rows, " + ("pushed into peer-mapped (CUDA IPC) buffers over NVLink, flag-ordered" if br.transport == "peer" else "NCCL p2p" + (f" (peer mapping unavailable: {br.fallback_reason})" if br.fallback_reason else ""))) if world > 1 else "single GPU",
-                       "band_edges": br.edges if br.edges is not None else "equal rows"},
+                       "band_edges": br.edges if br.edges is not None else "equal rows",
+                       "band_calibration": getattr(br, "calibration", None)},
             "gcandidates_per_s": W * H * feat.initialLightSamples * fps / 1e9,
             # the same count against the initial RIS pass alone (rank 0's band when the frame is sharded)
             "gcandidates_per_s_initial_pass": (round(px * feat.initialLightSamples / (per_pass["initial"]["ms_per_launch"] * 1e-3) / 1e9, 2)

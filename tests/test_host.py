@@ -108,3 +108,78 @@ def test_refine_band_edges_converges_with_latency_floor():
     t = times_of(edges)
     assert max(t) / np.mean(t) < 1.03 < spread0
     assert min(np.diff(edges)) >= 10 and edges[0] == 0 and edges[-1] == H
+
+
+def test_balance_over_a_camera_path_cuts_for_the_mean_profile():
+    """BASELINE C4 (orbiting camera) on several GPUs: the bands are cut once for the mean hit profile over cameras sampled along
+    the path, so that no row changes owner (and loses its temporal history) mid-sequence."""
+    import torch
+    from romis_b200.bands import BandedRenderer
+
+    class Stub:                                         # row_hit_counts of two very different views
+        def row_hit_counts(self, cam, W, H):
+            top = np.zeros(H); top[: H // 4] = W
+            bottom = np.zeros(H); bottom[H // 2:] = W
+            return top if cam == "up" else bottom
+
+    W, H = 64, 240
+    br = BandedRenderer.__new__(BandedRenderer)
+    br.r = Stub(); br.rank = 0; br.world_size = 3; br.edges = None; br._height = None
+    br.balance("up", W, H, 10)
+    only_up = list(br.edges)
+    br.balance(["up", "down"], W, H, 10)
+    mean = 0.5 * (Stub().row_hit_counts("up", W, H) + Stub().row_hit_counts("down", W, H))
+    assert br.edges == balanced_band_edges(mean + 0.04 * (W - mean), 3, 10)
+    assert br.edges != only_up and br.edges[0] == 0 and br.edges[-1] == H
+
+
+def test_search_band_edges_minimises_the_frame_time_not_the_stage_balance():
+    """The calibration's objective is the measured frame (slowest rank, passes overlapping), the per-band compute times only
+    propose cuts: on a model where equal compute times are NOT the fastest frame (one band hides part of its work behind the
+    overlap of its passes) and every measurement carries noise, the search must end near the true optimum, never stop at the
+    first cut because one noisy measurement looked balanced, and never return a cut slower than the one it started from."""
+    from romis_b200.bands import search_band_edges
+    H, world, a = 1080, 4, 0.12
+    y = np.arange(H)
+    cost = 0.3 + np.exp(-((y - 650) / 220.0) ** 2); cost *= 2.0 / cost.sum()
+    profile = np.maximum(cost * (1.0 + 0.25 * np.sin(y / 55.0)), 1e-3)
+    overlap = np.array([0.00, 0.06, 0.00, 0.03])           # part of a band's compute that the production frame hides
+    rng = np.random.default_rng(11)
+    calls = []
+
+    def evaluate(e, with_compute):
+        compute = np.array([a + cost[e[g]:e[g + 1]].sum() for g in range(world)])
+        frame = float(np.max(compute * (1.0 - overlap)))
+        calls.append(list(e))
+        return frame * (1.0 + 0.002 * rng.standard_normal()), list(compute * (1.0 + 0.004 * rng.standard_normal(world)))
+
+    true_frame = lambda e: max((a + cost[e[g]:e[g + 1]].sum()) * (1.0 - overlap[g]) for g in range(world))
+    start = [g * H // world for g in range(world)] + [H]
+    edges, ms, log = search_band_edges(start, evaluate, profile, 10)
+    # brute-force optimum of the noiseless model on a coarse grid around the answer is not needed: compare with the two natural cuts
+    from romis_b200.bands import refine_band_edges
+    balanced = list(start)
+    for _ in range(8):
+        balanced = refine_band_edges(balanced, [a + cost[balanced[g]:balanced[g + 1]].sum() for g in range(world)], profile, 10)
+    assert true_frame(edges) <= true_frame(start) and true_frame(edges) <= true_frame(balanced) * 1.002
+    assert true_frame(edges) < true_frame(balanced) * 0.995, "the polish must find what the stage balance cannot see"
+    assert len(log) == len(set(tuple(e) for e, _ in log)) <= 96 and len(calls) <= 2 * len(log)
+    assert min(np.diff(edges)) >= 10 and edges[0] == 0 and edges[-1] == H
+
+
+def test_search_band_edges_is_not_ended_by_a_lucky_first_measurement():
+    from romis_b200.bands import search_band_edges
+    H, world = 1080, 2
+    cost = np.where(np.arange(H) < 400, 2.0, 1.0); cost = cost / cost.sum()
+    first = [True]
+
+    def evaluate(e, with_compute):
+        t = [0.1 + cost[e[g]:e[g + 1]].sum() for g in range(world)]
+        if first[0]:                                    # the first measurement claims perfect balance
+            first[0] = False
+            return max(t), [np.mean(t)] * world
+        return max(t), t
+
+    edges, ms, log = search_band_edges([0, 540, H], evaluate, cost, 10)
+    best = min(range(10, H - 10), key=lambda c: max(cost[:c].sum(), cost[c:].sum()))
+    assert abs(edges[1] - best) <= 4 and len(log) > 1

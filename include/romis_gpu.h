@@ -132,9 +132,11 @@ typedef struct romis_rng {
  * n_devices > 1 makes a MULTI-DEVICE context for the reference's actual caller -- one thread of one process (main.cpp:164,
  * ui.cpp:161): the frame is cut into one row band per device (equal cost from the per-row hit profile), the bands' boundary
  * reservoir rows travel between neighbouring devices over NVLink inside the spatial pass (cudaDeviceEnablePeerAccess), and
- * romis_render_frame fills the caller's single out_rgb.  Results are bit-identical to the one-device frame.  On a multi-device
- * context the per-device calls (stepwise frames, bands, peer_*, R-MIS / R-OMIS frames, render_frame_device) return
- * ROMIS_ERR_INVALID; the same device may be listed twice (two bands on one GPU: a test configuration).
+ * romis_render_frame fills the caller's single out_rgb; romis_render_frame_rmis / _romis cut their frames the same way (each band
+ * renders its halo rows itself: nothing is exchanged) and leave the temporal history of a ReSTIR sequence alone, as the
+ * reference's previousFrameGrid outlives them (render.cpp:268-280).  Results are bit-identical to the one-device frame.  On a
+ * multi-device context the per-device calls (stepwise frames, bands, peer_*, render_frame_device, the R-MIS / R-OMIS parity
+ * read-backs) return ROMIS_ERR_INVALID; the same device may be listed twice (two bands on one GPU: a test configuration).
  * Replaces: EmbreeInterface construction + the implicit process state of the reference (main.cpp:56-65). */
 int romis_create(const int* device_ids, int n_devices, romis_ctx** out);
 void romis_destroy(romis_ctx* ctx);
@@ -198,7 +200,9 @@ float romis_specular_cutoff(float shininess);
  * spatial radius: random, or chosen by similarity of depth / normal / geometry, neighbour_selection.cpp), then
  * maxIterationsMIS rounds of { initial RIS per pixel; every pixel shades the samples of its k+1 neighbourhood pixels with
  * equal or balance-heuristic MIS weights and a shadow ray each }, averaged and tone mapped (combineToScreen,
- * render_utils.cpp:68-85).  No temporal state.  Whole frame on one context (bands are not supported for this mode).
+ * render_utils.cpp:68-85).  No temporal state.  With a row band set (romis_set_band) only the band's rows are rendered and
+ * written -- the band renders the radius rows around it itself, so bands need no exchange and, assembled, equal the whole frame
+ * bit for bit; a multi-device context does exactly that with one band per device.
  * ROMIS_NEIGHBOURS_DISSIMILAR is rejected: the reference passes a negative count to std::sample there
  * (neighbour_selection.cpp:88-93), which is undefined behaviour. */
 int romis_render_frame_rmis(romis_ctx* ctx, const romis_features* features, const romis_rmis_params* rmis,
@@ -215,7 +219,8 @@ int romis_download_rmis_neighbours(romis_ctx* ctx, int32_t* xy, uint32_t* count)
  * here include/romis_cod.h) whose components are summed, tone mapped and written in Screen layout (direct estimator).  With
  * useProgressiveROMIS the solves run before every progressiveUpdateMod-th iteration instead and a running estimate built from
  * the current alphas is averaged over the iterations (render.cpp:160-200,232).  numNeighboursToSample <= 10; every pixel's
- * window must hold k other pixels (the reference reads out of bounds otherwise, render.cpp:165).  Whole frame on one context. */
+ * window must hold k other pixels (the reference reads out of bounds otherwise, render.cpp:165).  Row bands and multi-device
+ * contexts as for R-MIS. */
 int romis_render_frame_romis(romis_ctx* ctx, const romis_features* features, const romis_rmis_params* rmis,
                              const romis_camera* camera, int width, int height, const romis_rng* rng, float* out_rgb);
 /* Parity read-back of the last R-OMIS frame: matrices[H][W][k+1][k+1] (row-major) and contributions[H][W][3][k+1]

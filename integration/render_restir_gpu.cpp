@@ -40,8 +40,6 @@ struct GpuState {
     romis_ctx* ctx = nullptr;
     const void* sceneKey = nullptr;     // identity of the uploaded geometry
     uint64_t sceneSig = 0;
-    bool multi = false;                 // several GPUs (ROMIS_DEVICES): R-MIS / R-OMIS frames use a one-device context of their own
-    romis_ctx* misCtx = nullptr; uint64_t misSig = 0; int misDevice = 0;
     bool sceneDirty = true;             // romis_dropin_invalidate_scene (hook next to EmbreeInterface::changeScene)
     uint64_t seed = 0x524f4d4953ull;    // "ROMIS"
     uint32_t frame = 0;
@@ -54,7 +52,6 @@ struct GpuState {
     void* pinnedPtr = nullptr; size_t pinnedBytes = 0; bool pinScreen = true;
     ~GpuState() {
         if (pinnedPtr) romis_host_unregister(pinnedPtr);
-        if (misCtx) romis_destroy(misCtx);
         if (ctx) romis_destroy(ctx);
     }
 };
@@ -228,7 +225,6 @@ static romis_camera prepare(const Scene& scene, const Trackball& camera) {
         }
         if (devs.empty()) devs.push_back(0);
         if (romis_create(devs.data(), (int)devs.size(), &g.ctx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
-        g.multi = devs.size() > 1; g.misDevice = devs[0];
     }
     // EmbreeInterface::changeScene (embree_interface.cpp:53-56) has no notification we could hook: detect geometry changes
     const uint64_t sig = geometrySignature(scene);
@@ -244,18 +240,6 @@ static romis_camera prepare(const Scene& scene, const Trackball& camera) {
     cam.half_width = g_halfW; cam.half_height = g_halfH;
     if (g_halfH == 0.0f) throw std::runtime_error("romis drop-in: image-plane half extents not set (romis_dropin_set_half_extents)");
     return cam;
-}
-
-// R-MIS / R-OMIS frames are not sharded: with several GPUs configured they run on a one-device context of their own
-static romis_ctx* misContext(const Scene& scene) {
-    if (!g.multi) return g.ctx;
-    if (!g.misCtx && romis_create(&g.misDevice, 1, &g.misCtx) != ROMIS_OK) throw std::runtime_error(std::string("romis_create: ") + romis_last_error(nullptr));
-    const uint64_t sig = geometrySignature(scene);
-    if (g.misSig != sig) { uploadScene(g.misCtx, scene); g.misSig = sig; }
-    std::vector<romis_light> lights(scene.lights.size());
-    for (size_t i = 0; i < lights.size(); i++) lights[i] = toPod(scene.lights[i]);
-    if (romis_upload_lights(g.misCtx, lights.data(), (int)lights.size()) != ROMIS_OK) throw std::runtime_error(std::string("romis_upload_lights: ") + romis_last_error(g.misCtx));
-    return g.misCtx;
 }
 
 ReservoirGrid ROMIS_DROPIN_NAME(std::shared_ptr<ReservoirGrid> previousFrameGrid,
@@ -303,7 +287,7 @@ void ROMIS_DROPIN_RMIS_NAME(const Scene& scene, const Trackball& camera, const E
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    romis_ctx* ctx = misContext(scene);
+    romis_ctx* ctx = g.ctx;             // one device, or one row band per device under ROMIS_DEVICES: same call
     if (romis_render_frame_rmis(ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)) != ROMIS_OK)
         throw std::runtime_error(std::string("romis_render_frame_rmis: ") + romis_last_error(ctx));
 }
@@ -316,7 +300,7 @@ void ROMIS_DROPIN_ROMIS_NAME(const Scene& scene, const Trackball& camera, const 
     const romis_features f = toPod(features);
     const romis_rmis_params p = toMisPod(features);
     romis_rng rng { g.seed, g.frame++, 0 };
-    romis_ctx* ctx = misContext(scene);
+    romis_ctx* ctx = g.ctx;
     if (romis_render_frame_romis(ctx, &f, &p, &cam, res.x, res.y, &rng, screenStorage(screen)) != ROMIS_OK)
         throw std::runtime_error(std::string("romis_render_frame_romis: ") + romis_last_error(ctx));
 }

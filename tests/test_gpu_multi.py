@@ -139,7 +139,8 @@ def test_multi_device_context_renders_mis_frames_and_keeps_the_restir_history(n)
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libromis_dropin.so")), reason="oracle/_ref/libromis_dropin.so not built")
 def test_dropin_on_two_devices_fills_the_reference_screen():
     """integration/render_restir_gpu.cpp with ROMIS_DEVICES=a,b (own process: the drop-in creates its context once per thread):
-    Screen::pixels() equals the compiled reference's renderReSTIR bit for bit."""
+    Screen::pixels() equals the compiled reference's renderReSTIR bit for bit; so does renderRMIS through the same context, and
+    the ReSTIR sequence continues from its history afterwards as the reference's does."""
     devs = ",".join(str(d) for d in _devices(2))
     code = ("import sys; sys.path[:0] = ['tests', 'tests/golden']\n"
             "from oracle import pyoracle; from romis_b200.scene import Features; from cases import NIGHTCLUB_CAM; from common import assert_bits_equal, load_scene\n"
@@ -149,6 +150,12 @@ def test_dropin_on_two_devices_fills_the_reference_screen():
             "    cpu = lib.render_frame(feat, NIGHTCLUB_CAM, 96, 80, fr > 0, 314, fr, pyoracle.REF_FLAG_WHOLE_FRAME, dump=False).image\n"
             "    gpu = lib.render_frame_gpu(feat, NIGHTCLUB_CAM, 96, 80, fr > 0, 314, fr)\n"
             "    assert_bits_equal(gpu, cpu, f'frame {fr}')\n"
+            "from romis_b200.scene import RmisParams\n"
+            "rp = RmisParams(maxIterationsMIS=2)\n"
+            "cpu = lib.render_frame_rmis(feat, rp, NIGHTCLUB_CAM, 96, 80, 2718, 1, False)[0]\n"
+            "assert_bits_equal(lib.render_frame_mis_gpu(False, feat, rp, NIGHTCLUB_CAM, 96, 80, 2718, 1), cpu, 'renderRMIS on the device group')\n"
+            "cpu = lib.render_frame(feat, NIGHTCLUB_CAM, 96, 80, True, 314, 3, pyoracle.REF_FLAG_WHOLE_FRAME, dump=False).image\n"
+            "assert_bits_equal(lib.render_frame_gpu(feat, NIGHTCLUB_CAM, 96, 80, True, 314, 3), cpu, 'ReSTIR frame 3 after the R-MIS frame: history kept')\n"
             "print('dropin on devices " + devs + " ok')\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, ROMIS_DEVICES=devs))
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(S
         if (threadIdx.x == 0 && threadIdx.y == 0) {
             if (edge0) halo_spin(hd.wait_flag[0], hd.wait_token, hd.err);
             if (edge1) halo_spin(hd.wait_flag[1], hd.wait_token, hd.err);
-            __threadfence_system();
+            fence_acquire_sys();                    // the neighbour's rows in my halo: no stale line of them may stay in this SM's L1
         }
         __syncthreads();
     }
@@ -144,9 +144,13 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_SPATIAL) spatial_halo_kernel(S
     spatial_pixel<NT, UNBIASED, ES>(sc, fr, g, in, out, pass, x, y, &hd, fd, gy0, gy1);
     fine_signal(fd, gy0, gy1);
     if (edge0 || edge1) {
-        __threadfence_system();
+        // Release pattern: every thread's stores (own buffer and the neighbour's halo over NVLink), the barrier, then ONE release
+        // fence in thread 0 -- cumulative over what the barrier made it observe -- and its counter update; the last block of an edge
+        // reads all the others' updates, fences both ways and publishes the token.  (Round 2: this was a fence.sc.sys by every
+        // thread of every edge block, each one also invalidating the L1 under the two other blocks resident on the SM.)
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
+            fence_release_sys();
             _Pragma("unroll") for (int e = 0; e < 2; e++) {
                 if (!(e == 0 ? edge0 : edge1)) continue;
                 if (atomicAdd(&hd.counter[e], 1u) == hd.edge_blocks[e] - 1u) {

@@ -182,9 +182,15 @@ def run_reference(args, label, scene, W, H, feat, cam, rank, world):
     w, h = W // div, H // div
     scale = (w * h) / float(W * H)
 
+    last = [None]
+
     def frame(fr, ww, hh):
+        # history only from a frame of the same size: the reference indexes previousFrameGrid with the new frame's pixels
+        # (render_utils.cpp:154), so a predecessor of another resolution is an out-of-bounds read, not a reset
+        hist = last[0] == (ww, hh)
+        last[0] = (ww, hh)
         t0 = time.perf_counter()
-        ref.render_frame(feat, camera_for_frame(args.config, cam, fr), ww, hh, fr > 0, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
+        ref.render_frame(feat, camera_for_frame(args.config, cam, fr), ww, hh, hist, SEED, fr, REF_FLAG_TIMING_RNG, dump=False, want_image=True)
         return time.perf_counter() - t0
     fr = 0
     for _ in range(max(0, args.warmup - 1)):
@@ -284,7 +290,7 @@ def run_mis(args, mode, rank, world):
         if rank != 0:
             return                                      # rank 0 alone runs the CPU reference
         from oracle.pyoracle import RefLib
-        ref = RefLib(); ref.set_scene(scene); ref.set_mis_timing(True)
+        ref = RefLib(); ref.lib.ref_set_num_threads(host_cores()); ref.set_scene(scene); ref.set_mis_timing(True)   # torchrun exports OMP_NUM_THREADS=1
         div = 8
         w, h = W // div, H // div
         scale = (w * h) / float(W * H)

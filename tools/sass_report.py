@@ -16,7 +16,8 @@ only = re.compile(sys.argv[3]) if len(sys.argv) > 3 else None
 GROUPS = [("LDS", r"^LDS"), ("STS", r"^STS"), ("SHFL", r"^SHFL"), ("VOTE/MATCH", r"^(VOTE|MATCH|WARPSYNC)"), ("LDL", r"^LDL"), ("STL", r"^STL"),
           ("LDG", r"^LDG"), ("STG", r"^STG"), ("DMUL/DADD/DFMA", r"^(DMUL|DADD|DFMA)"), ("MUFU", r"^MUFU"), ("FFMA", r"^FFMA"),
           ("FMUL/FADD", r"^(FMUL|FADD)"), ("IMAD/LOP3/SHF", r"^(IMAD|LOP3|SHF|IADD3)"), ("BSSY/BSYNC", r"^(BSSY|BSYNC)"), ("CALL", r"^CALL"),
-          ("UTMALDG/UTMASTG", r"^UTMA"), ("total", r"^[A-Z]")]
+          ("UTMALDG/UTMASTG", r"^UTMA"), ("MEMBAR.SC", r"^MEMBAR\.SC"), ("MEMBAR.ALL", r"^MEMBAR\.ALL"), ("CCTL.IVALL", r"^CCTL\.IVALL"),
+          ("total", r"^[A-Z]")]
 
 
 def demangle(names):
@@ -67,7 +68,10 @@ rows.sort(key=lambda r: r[0])
 hdr = ["kernel", "regs", "stack B", "local B", "static smem B"] + [g for g, _ in GROUPS]
 lines = ["# SASS / resource listing of `%s`" % lib, "",
          "Static instruction counts from `cuobjdump -sass` (sm_100a cubins), resources from `cuobjdump -res-usage`; produced by",
-         "`tools/sass_report.py`.  stack B = per-thread local memory the compiler reserved (traversal stacks, generic-N arrays, spills).", "",
+         "`tools/sass_report.py`.  stack B = per-thread local memory the compiler reserved (traversal stacks, generic-N arrays, spills).",
+         "MEMBAR.SC / MEMBAR.ALL / CCTL.IVALL: what the fences of the row-group counters and of the halo tokens compile to -- `__threadfence()`",
+         "is MEMBAR.SC *and* CCTL.IVALL (the SM's whole L1 invalidated); `fence.release` is MEMBAR.ALL alone, `fence.acquire` CCTL.IVALL alone",
+         "(DESIGN.md 4, 6).  The MEMBAR.SC left are the once-per-edge-and-pass token publishers and the stand-alone flag kernels.", "",
          "| " + " | ".join(hdr) + " |", "|" + "---|" * len(hdr)]
 for s, reg, st, loc, sh, c in rows:
     lines.append("| `%s` | %d | %d | %d | %d | " % (s, reg, st, loc, sh) + " | ".join(str(c[g]) for g, _ in GROUPS) + " |")

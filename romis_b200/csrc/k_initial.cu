@@ -10,8 +10,12 @@ namespace romis {
 // EXTRA (R-OMIS): also writes wSums and chosenSampleWeights (reservoir.h:38-41), which
 // arbitraryUnbiasedContributionWeightReciprocal reads (render_utils.cpp:245-257), as N planes each.
 template <int NT, bool EXTRA>
-__device__ __forceinline__ void initial_pixel(const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out, float* __restrict__ wsum,
-                                              float* __restrict__ chosen, int x, int y) {
+__global__ void __launch_bounds__(ROMIS_LBT_INITIAL, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out, float* __restrict__ wsum, float* __restrict__ chosen) {
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
+    pdl_wait();                                     // the G-buffer comes from the kernel before this one
+    pdl_launch_dependents();
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = fr.f.enableShading != 0;
     const uint32_t pixel = (uint32_t)y * (uint32_t)fr.W + (uint32_t)x;
@@ -65,24 +69,10 @@ __device__ __forceinline__ void initial_pixel(const SceneDev& sc, const FrameDev
     store_extra();
 }
 
-// fd.sig_ctr: the warps count themselves per row group when they are done, so that the temporal pass (same pixel, nothing else of
-// this pass) starts on the rows that are ready while the long tail of this kernel -- a thread runs for ~100 us, and the last wave
-// of blocks leaves the SMs a few warps at a time -- is still draining (device_common.cuh "row-group completion counters").
-template <int NT, bool EXTRA>
-__global__ void __launch_bounds__(ROMIS_LBT_INITIAL, ROMIS_MINB_INITIAL) initial_kernel(SceneDev sc, FrameDev fr, GBufDev g, ResBuf out, float* __restrict__ wsum, float* __restrict__ chosen, FineDev fd) {
-    int x, y; thread_pixel<false>(x, y);
-    y += fr.y0;
-    if (x >= fr.W || y >= fr.y1) return;
-    pdl_wait();                                     // the G-buffer comes from the kernel before this one
-    pdl_launch_dependents();
-    initial_pixel<NT, EXTRA>(sc, fr, g, out, wsum, chosen, x, y);
-    fine_signal_rows(fd, y);
-}
-
 
 void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
-                    const FineDev& fd, float* wsum, float* chosen) {
-    if (wsum && chosen) { ROMIS_DISPATCH_N(N, (launch_pdl(initial_kernel<NT, true>, grid, block, s, sc, fr, g, out, wsum, chosen, fd))); }
-    else { ROMIS_DISPATCH_N(N, (launch_pdl(initial_kernel<NT, false>, grid, block, s, sc, fr, g, out, (float*)nullptr, (float*)nullptr, fd))); }
+                    float* wsum, float* chosen) {
+    if (wsum && chosen) { ROMIS_DISPATCH_N(N, (launch_pdl(initial_kernel<NT, true>, grid, block, s, sc, fr, g, out, wsum, chosen))); }
+    else { ROMIS_DISPATCH_N(N, (launch_pdl(initial_kernel<NT, false>, grid, block, s, sc, fr, g, out, (float*)nullptr, (float*)nullptr))); }
 }
 }  // namespace romis

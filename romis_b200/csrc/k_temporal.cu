@@ -13,12 +13,7 @@ __global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) tempo
     y += fr.y0;
     if (x >= fr.W || y >= fr.y1) return;
     const int by0 = fr.y0 + (int)(blockIdx.y * blockDim.y), by1 = by0 + (int)blockDim.y;
-    // `cur` comes from the kernel before this one, the initial pass: its row groups of this block's rows (the whole kernel without counters)
-#ifdef ROMIS_TEMPORAL_STRONG
-    fine_wait_rows<false>(fd, y);
-#else
-    fine_wait_rows(fd, y);
-#endif
+    pdl_wait();                                     // `cur` comes from the kernel before this one
     pdl_launch_dependents();
     const int N = NT > 0 ? NT : (int)fr.f.numSamplesInReservoir;
     const bool es = ES || fr.f.enableShading != 0;
@@ -28,11 +23,7 @@ __global__ void __launch_bounds__(ROMIS_LBT_TEMPORAL, ROMIS_MINB_TEMPORAL) tempo
     uint4 crec[CAP], prec[CAP]; uint32_t cM[CAP], pM[CAP]; float cpdf[CAP];
     uint64_t curTotal = 0, prevTotal = 0;
     ROMIS_FOR_SUB(j, NT, N) {
-#ifdef ROMIS_TEMPORAL_STRONG
-        crec[j] = __ldcg(res_rec(cur, lrow, j) + x); cM[j] = __ldcg(res_m(cur, lrow, j) + x); cpdf[j] = __ldcg(res_pdf(cur, lrow, j) + x);
-#else
         crec[j] = res_rec(cur, lrow, j)[x]; cM[j] = res_m(cur, lrow, j)[x]; cpdf[j] = res_pdf(cur, lrow, j)[x];
-#endif
         prec[j] = res_rec(prev, lrow, j)[x]; pM[j] = res_m(prev, lrow, j)[x];
         curTotal += cM[j]; prevTotal += pM[j];
     }

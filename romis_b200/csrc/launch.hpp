@@ -20,7 +20,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
 }
 void launch_primary(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1);
 void launch_initial(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, const ResBuf& out,
-                    const FineDev& fd, float* wsum = nullptr, float* chosen = nullptr);
+                    float* wsum = nullptr, float* chosen = nullptr);
 void launch_temporal(cudaStream_t s, dim3 grid, dim3 block, int N, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,
                      const ResBuf& cur, const ResBuf& prev, const ResBuf& out, const FineDev& fd, const HaloDev& hd);
 void launch_spatial(cudaStream_t s, dim3 grid, dim3 block, int N, bool unbiased, const SceneDev& sc, const FrameDev& fr, const GBufDev& g,

@@ -658,26 +658,15 @@ static bool fine_enabled(const romis_ctx* c) {
     const long long blocks = (long long)((c->W + 31) / 32) * ((c->y1 - c->y0 + (int)kBlock.y - 1) / (int)kBlock.y);
     return blocks < 4LL * c->n_sms * ROMIS_MINB_SPATIAL;
 }
-// The link initial pass -> temporal pass (the temporal pass reads nothing but its own pixel's initial reservoir, and the tail of the
-// initial pass is the longest of the frame) has its own switch and warp-granular counting (fine_signal_rows / fine_wait_rows).
-// Measured on B200, C2: it LOSES -- counted per block (barrier + fence + atomic) the initial pass goes 0.970 -> 1.039 ms, because
-// the barrier keeps the registers of finished warps until the block's slowest warp is through; counted per warp (no barrier) it
-// goes 0.977 -> 1.101 ms: a __threadfence() per warp costs more than the tail it uncovers (full frame 2.469 -> 2.573 ms, 135-row
-// band 0.546 -> 0.585 ms).  Off unless ROMIS_FINE_INITIAL=1.
-#define ROMIS_FINE_STAGE_INITIAL (ROMIS_FINE_STAGES - 1)     // stage ids: 0 temporal, 1 + p spatial pass p (p <= 61), 64 initial
-static bool fine_initial_enabled(const romis_ctx* c) {
-    static const bool on = [] { const char* e = std::getenv("ROMIS_FINE_INITIAL"); return e && std::atoi(e) != 0; }();
-    return on && kBlockS.y == 4 && c->W;
-}
-static bool fine_link(const romis_ctx* c, int stage) { return stage == ROMIS_FINE_STAGE_INITIAL ? fine_initial_enabled(c) : fine_enabled(c); }
 static FineDev fine_for(romis_ctx* c, int consume, int produce, int reach) {
     FineDev fd; std::memset(&fd, 0, sizeof fd);
     fd.y0 = c->y0; fd.y1 = c->y1; fd.reach = reach;
     unsigned int* base = (unsigned int*)c->fine_ctr.p;
     fd.err = (uint32_t*)(base + (size_t)ROMIS_FINE_STAGES * c->fine_groups);
     const unsigned int per_group = (unsigned int)((c->W + 31) / 32);        // blocks are 32 pixels wide
-    if (consume >= 0 && fine_link(c, consume)) { fd.wait_ctr = base + (size_t)consume * c->fine_groups; fd.wait_target = per_group * c->fine_count[consume]; }
-    if (produce >= 0 && fine_link(c, produce)) { fd.sig_ctr = base + (size_t)produce * c->fine_groups; c->fine_count[produce]++; }
+    if (!fine_enabled(c)) return fd;
+    if (consume >= 0) { fd.wait_ctr = base + (size_t)consume * c->fine_groups; fd.wait_target = per_group * c->fine_count[consume]; }
+    if (produce >= 0) { fd.sig_ctr = base + (size_t)produce * c->fine_groups; c->fine_count[produce]++; }
     return fd;
 }
 
@@ -760,9 +749,7 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     c->fine_src = -1;           // which stage's counters the next pass may wait on (-1: wait for the whole previous kernel)
     // 2. initial RIS (+ visibility reuse)
     const bool with_temporal = f->temporalReuse && c->history_valid;
-    // its warps count themselves per row group for the temporal pass (fine_signal_rows / fine_wait_rows)
-    const bool count_initial = with_temporal && fine_initial_enabled(c);
-    launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), fine_for(c, -1, count_initial ? ROMIS_FINE_STAGE_INITIAL : -1, 0));
+    launch_initial(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0));
     c->n_launches++;
     RCHECK(c, cudaGetLastError());
     RCHECK(c, mark(c, 2, 0));
@@ -772,8 +759,7 @@ extern "C" int romis_frame_begin(romis_ctx* c, const romis_features* f, const ro
     if (with_temporal) {
         HaloDev hd; std::memset(&hd, 0, sizeof hd);
         if ((c->peer[0].on || c->peer[1].on) && f->spatialReuse && f->spatialResamplingPasses > 0) { hd = halo_for_stage0(c, w0, gOwn, kBlockS); c->stage0_pushed = true; }
-        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0),
-                        fine_for(c, count_initial ? ROMIS_FINE_STAGE_INITIAL : -1, 0, 0), hd);
+        launch_temporal(c->stream, gOwn, kBlockS, c->N, c->sc, c->fr, gbuf(c), resbuf(c, w0), resbuf(c, c->hist), resbuf(c, w0), fine_for(c, -1, 0, 0), hd);
         c->fine_src = fine_enabled(c) ? 0 : -1;
         c->n_launches++;
         RCHECK(c, cudaGetLastError());
@@ -1380,7 +1366,7 @@ static int render_mis_enqueue(romis_ctx* c, int mode, const romis_features* f, c
     RCHECK(c, cudaGetLastError());
     for (uint32_t it = 0; it < rp->maxIterationsMIS; it++) {                                // :72 / :141
         fr.initial_stage = frH.initial_stage = ROMIS_STAGE_RMIS_INITIAL0 + it;
-        launch_initial(c->stream, gridH, kBlockS, c->N, c->sc, frH, g, resbuf(c, work), FineDev{}, rm.wsum, rm.chosen);    // :74 / :143
+        launch_initial(c->stream, gridH, kBlockS, c->N, c->sc, frH, g, resbuf(c, work), rm.wsum, rm.chosen);    // :74 / :143
         RCHECK(c, mark(c, 8, (int)it));
         if (mode == 0) launch_rmis_gather(c->stream, gridS, kBlockS, c->N, c->sc, fr, g, resbuf(c, work), rm);
         else if (rp->useProgressiveROMIS && it >= 1u && it % rp->progressiveUpdateMod == 0u) {                  // :160-164

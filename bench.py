@@ -89,6 +89,9 @@ def pass_bytes(N: int):
     return {"primary": 20, "initial": 20 + 20 * N, "temporal": 20 + 60 * N, "spatial": 20 + 40 * N, "shade": 32 + 20 * N}
 
 
+CLOCK_POLL_S = float(os.environ.get("ROMIS_CLOCK_POLL_MS", "2")) * 1e-3
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed legs, polled through NVML every ~2 ms from a thread (nvidia-smi -lms
     needs ~1 s to start and then misses a 12 ms region).  Only samples taken between begin() and end() count."""
@@ -124,7 +127,7 @@ class ClockSampler:
                     self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons(self.h))))
                 except Exception:   # noqa: BLE001
                     pass
-            time.sleep(0.002)
+            time.sleep(CLOCK_POLL_S)
 
     def stop(self):
         self.stop_flag = True

@@ -3,9 +3,11 @@
 // neighbourhood pixels with equal or balance-heuristic MIS weights (render.cpp:79-112; generalisedBalanceHeuristic,
 // render_utils.cpp:179-187) and combineToScreen (render_utils.cpp:68-85).  The initial RIS of every iteration is
 // initial_kernel (k_initial.cu) under the iteration's own random-stream stage.
+#include <cstdlib>
 #include "reservoir.cuh"
 #include "launch.hpp"
 #include "romis_cod.h"
+#include "cod_fixed.hpp"
 
 namespace romis {
 
@@ -412,6 +414,14 @@ __global__ void __launch_bounds__(256, ROMIS_MINB_RMIS) romis_accumulate_kernel(
 // (solveSystem = completeOrthogonalDecomposition().solve, render_utils.h:52 -> include/romis_cod.h), component sums,
 // tone mapping, Screen layout.
 // alphas_only: the progressive estimator's per-iteration update of the alpha vectors (:160-164) instead of the image.
+// Common tail of both solve kernels: component sums, tone mapping, Screen layout (render.cpp:247-262)
+__device__ __forceinline__ void romis_write_pixel(const FrameDev& fr, float* __restrict__ rgb, int x, int y, const float* sum) {
+    v3 color = V3(sum[0], sum[1], sum[2]);
+    if (fr.f.enableToneMapping) color = tone_map(color, fr.f);                      // tone_mapping.cpp:8-11
+    size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;
+    rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
+}
+
 __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb, int alphas_only) {
     int x, y; thread_pixel<false>(x, y);
     y += fr.y0;
@@ -440,10 +450,41 @@ __global__ void __launch_bounds__(128) romis_solve_kernel(FrameDev fr, RmisDev r
         sum[ch] = s;
     }
     if (alphas_only) return;
-    v3 color = V3(sum[0], sum[1], sum[2]);
-    if (fr.f.enableToneMapping) color = tone_map(color, fr.f);                      // tone_mapping.cpp:8-11
-    size_t i = (size_t)(fr.H - 1 - y) * fr.W + x;
-    rgb[3 * i] = color.x; rgb[3 * i + 1] = color.y; rgb[3 * i + 2] = color.z;
+    romis_write_pixel(fr, rgb, x, y, sum);
+}
+
+// The same for a system size known at compile time (K1 = 6: the reference's default k = 5): cod_fixed.hpp, the decomposition in
+// registers.  Bit-identical to the generic kernel (tests/test_cod_fixed.py on the CPU, tests/test_gpu_romis.py against the oracle).
+template <int K1>
+__global__ void __launch_bounds__(128) romis_solve_fixed_kernel(FrameDev fr, RmisDev rm, float* __restrict__ rgb, int alphas_only) {
+    int x, y; thread_pixel<false>(x, y);
+    y += fr.y0;
+    if (x >= fr.W || y >= fr.y1) return;
+    const size_t p = (size_t)y * fr.W + x;
+    CodFixed<K1> cod;
+    bool any = false;
+    _Pragma("unroll") for (int i = 0; i < K1; i++) {
+        _Pragma("unroll") for (int b = i; b < K1; b++) {
+            const float t = rm.tech[(size_t)(i * K1 + b) * rm.plane + p];
+            cod.qr[i][b] = t; cod.qr[b][i] = t;
+            any |= t != 0.0f;
+        }
+    }
+    float sum[3] = {0.0f, 0.0f, 0.0f};
+    if (any) {
+        cod_fixed_solve3<K1>(cod,
+            [&](int ch, float* b) { _Pragma("unroll") for (int i = 0; i < K1; i++) b[i] = rm.contrib[(size_t)(ch * K1 + i) * rm.plane + p]; },
+            [&](int ch, const float* xs) {
+                if (alphas_only) { _Pragma("unroll") for (int i = 0; i < K1; i++) rm.alpha[(size_t)(ch * K1 + i) * rm.plane + p] = xs[i]; return; }
+                float s = 0.0f;
+                _Pragma("unroll") for (int i = 0; i < K1; i++) s += xs[i];              // :247-252
+                if (ch == 0) sum[0] = s; else if (ch == 1) sum[1] = s; else sum[2] = s;
+            });
+    } else if (alphas_only) {                       // all-zero system: rank 0, x = 0 (see the generic kernel)
+        for (int i = 0; i < 3 * K1; i++) rm.alpha[(size_t)i * rm.plane + p] = 0.0f;
+    }
+    if (alphas_only) return;
+    romis_write_pixel(fr, rgb, x, y, sum);
 }
 
 void launch_ctx(cudaStream_t s, dim3 grid, dim3 block, const SceneDev& sc, const FrameDev& fr, const GBufDev& g, int row0, int row1) {
@@ -461,7 +502,10 @@ void launch_romis_accumulate(cudaStream_t s, dim3 grid, dim3 block, int N, const
 }
 void launch_romis_solve(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb, bool alphas_only) {
     dim3 b(32, 4), gr((fr.W + 31) / 32, (fr.y1 - fr.y0 + 3) / 4);
-    romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb, alphas_only ? 1 : 0);
+    // ROMIS_SOLVE_GENERIC=1 (environment): the local-memory routine for every size (A/B runs)
+    static const bool generic_only = [] { const char* e = std::getenv("ROMIS_SOLVE_GENERIC"); return e && std::atoi(e) != 0; }();
+    if (rm.K1 == 6 && !generic_only) romis_solve_fixed_kernel<6><<<gr, b, 0, s>>>(fr, rm, rgb, alphas_only ? 1 : 0);
+    else romis_solve_kernel<<<gr, b, 0, s>>>(fr, rm, rgb, alphas_only ? 1 : 0);
 }
 void launch_rmis_combine(cudaStream_t s, dim3 grid, dim3 block, const FrameDev& fr, const RmisDev& rm, float* rgb) {
     rmis_combine_kernel<<<grid, block, 0, s>>>(fr, rm, rgb);

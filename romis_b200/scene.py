@@ -74,6 +74,9 @@ class RmisParams:
                                      int(self.progressiveUpdateMod))
 
 
+_CAMERA_CACHE = {}
+
+
 @dataclass
 class Camera:
     """`CameraConfig` of the reference (src/utils/config.h:21-26); defaults = the nightclub view."""
@@ -84,7 +87,21 @@ class Camera:
 
     def to_abi(self, width: int, height: int) -> abi.romis_camera:
         """origin = Trackball::position() (framework/src/trackball.cpp:75-78), quat = glm::quat(euler)
-        (glm type_quat.inl:208-217), half extents per trackball.cpp:26-27; all in fp32."""
+        (glm type_quat.inl:208-217), half extents per trackball.cpp:26-27; all in fp32.
+        The numpy scalar arithmetic below costs ~60 us, which sits in front of a frame's first kernel launch (the reference's
+        Trackball computes these once per camera change, not per frame): results are kept per (camera, resolution)."""
+        key = (float(self.fov_deg), float(self.distance), tuple(float(t) for t in self.look_at),
+               tuple(float(t) for t in self.rotation_deg), int(width), int(height))
+        hit = _CAMERA_CACHE.get(key)
+        if hit is None:
+            if len(_CAMERA_CACHE) >= 4096:
+                _CAMERA_CACHE.clear()
+            hit = _CAMERA_CACHE[key] = self._to_abi(width, height)
+        cam = abi.romis_camera()
+        C.memmove(C.byref(cam), C.byref(hit), C.sizeof(cam))       # callers own (and may edit) what they get
+        return cam
+
+    def _to_abi(self, width: int, height: int) -> abi.romis_camera:
         f32 = np.float32
         rad = [f32(math.radians(1.0)) * f32(a) for a in self.rotation_deg]   # glm::radians: deg * 0.0174532925...
         c = [f32(np.cos(f32(a) * f32(0.5))) for a in rad]

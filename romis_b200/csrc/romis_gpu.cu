@@ -651,6 +651,8 @@ static dim3 grid_for(int W, int rows, const dim3& b = kBlock) { return dim3((W +
 // (measured on B200, C2: temporal +12 %, spatial pass +20 % on the full 1080p frame), the gain is the drained tail of each pass --
 // a fixed ~25 us per frame.  It pays on thin bands only (135 rows: 0.573 -> 0.548 ms; full frame: 2.50 -> 2.73 ms), so by default
 // it is on when the spatial grid is fewer than 4 waves of resident blocks.  ROMIS_FINE=0 / 1 forces it off / on.
+// (Re-measured with the one-directional fences: 135 rows 0.574 -> 0.539 ms, 270 rows 0.943 -> 0.940 ms, 540 rows 1.588 -> 1.668 ms,
+// full frame 2.468 -> 2.650 ms: the threshold stands.)
 static bool fine_enabled(const romis_ctx* c) {
     static const int mode = [] { const char* e = std::getenv("ROMIS_FINE"); return e ? (std::atoi(e) != 0 ? 1 : 0) : -1; }();
     if (mode == 0 || kBlock.y % 4 != 0 || kBlockS.y % 4 != 0 || !c->W) return false;

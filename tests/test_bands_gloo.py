@@ -44,3 +44,73 @@ def _worker(rank, world, port, H, W, radius, passes, out_dir):
 def test_halo_exchange_over_gloo(world, H, radius, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), H, 17, radius, 3, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}.npy").exists() for r in range(world))
+
+
+# ---- the band calibration as a collective: every rank measures its own band, all gather, all take the same decisions ----
+class _Timings:
+    def __init__(self, compute, total):
+        self.primary_ms = 0.0; self.initial_ms = compute; self.temporal_ms = 0.0; self.shade_ms = 0.0
+        self.spatial_ms = [0.0]; self.n_spatial = 0; self.total_ms = total
+
+
+class _StubRenderer:
+    """Stands in for RestirRenderer: a band's time is a latency floor plus the cost of its rows, with rank-dependent noise."""
+
+    def __init__(self, rank, cost):
+        self.rank, self.cost, self.band, self.stage = rank, cost, (0, len(cost)), False
+        self.rng = np.random.default_rng(100 + rank); self.frames = 0
+
+    def row_hit_counts(self, cam, W, H):
+        return np.asarray(self.cost) * W
+
+    def set_stage_timing(self, on): self.stage = on
+    def synchronize(self): pass
+    def reset_history(self): pass
+
+    def timings(self):
+        t = 0.15 + float(np.sum(self.cost[self.band[0]:self.band[1]])) * (1.0 + 0.003 * self.rng.standard_normal())
+        return _Timings(t, t * (0.97 if self.rank == 0 else 1.0))     # rank 0 hides part of its work in the production frame
+
+
+def _calibrate_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from romis_b200.bands import BandedRenderer
+        from romis_b200.scene import Features
+        H, W = 360, 64
+        y = np.arange(H)
+        cost = (0.3 + np.exp(-((y - 230) / 70.0) ** 2)); cost = cost / cost.sum()
+
+        class Stub(BandedRenderer):
+            def render_frame(self, features, camera, W, H, history_valid, seed, frame, out=None):
+                self.r.band = self.band(H); self.r.frames += 1
+
+        br = Stub.__new__(Stub)
+        br.r = _StubRenderer(rank, cost); br.rank, br.world_size = rank, world
+        br._attached = None; br._height = None; br.edges = None; br.transport = "none"
+        feat = Features(spatialResamplingPasses=1)
+        br.balance("cam", W, H, feat.spatialResampleRadius)
+        first = list(br.edges)
+        calls = []
+        br.calibrate(feat, "cam", W, H, before_frame=lambda: calls.append(1))
+        every = [None] * world
+        dist.all_gather_object(every, (br.edges, br.calibration["frame_ms"], br.r.frames, len(calls)))
+        assert all(e[0] == every[0][0] for e in every), f"ranks ended on different cuts: {every}"
+        assert all(e[2] == every[0][2] for e in every), "ranks rendered different numbers of frames (a collective would hang)"
+        assert every[0][3] == br.r.frames, "before_frame runs ahead of every measured frame"
+        e = br.edges
+        assert e[0] == 0 and e[-1] == H and min(np.diff(e)) >= feat.spatialResampleRadius
+        t = [0.15 + cost[e[g]:e[g + 1]].sum() for g in range(world)]
+        t0 = [0.15 + cost[first[g]:first[g + 1]].sum() for g in range(world)]
+        assert max(t) <= max(t0) * 1.002 and max(t) / np.mean(t) < 1.06, (e, t)
+        np.save(os.path.join(out_dir, f"cal{rank}.npy"), np.array(e))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_calibration_is_a_consistent_collective(world, tmp_path):
+    mp.spawn(_calibrate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cuts = [np.load(tmp_path / f"cal{r}.npy") for r in range(world)]
+    assert all(np.array_equal(c, cuts[0]) for c in cuts)

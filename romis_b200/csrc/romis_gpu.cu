@@ -1421,7 +1421,13 @@ static int group_render_mis(romis_ctx* g, int mode, const romis_features* f, con
         for (int i = 0; i < active; i++) if ((rc = romis_set_band(g->kids[i], (*edges)[i], (*edges)[i + 1]))) return group_fail(g, g->kids[i], rc);
         g->g_active = active;
     }
-    for (int i = 0; i < active; i++) if ((rc = render_mis_enqueue(g->kids[i], mode, f, rp, cam, W, H, rng, out_rgb, reuse))) return group_fail(g, g->kids[i], rc);
+    for (int i = 0; i < active; i++) {
+        if ((rc = render_mis_enqueue(g->kids[i], mode, f, rp, cam, W, H, rng, out_rgb, reuse))) {
+            // the devices before this one already copy into the caller's image: not behind the caller's back after the call returns
+            for (int j = 0; j < i; j++) { cudaSetDevice(g->kids[j]->device); cudaStreamSynchronize(g->kids[j]->stream); }
+            return group_fail(g, g->kids[i], rc);
+        }
+    }
     for (int i = 0; i < active; i++) {
         romis_ctx* k = g->kids[i];
         cudaSetDevice(k->device);
